@@ -1,0 +1,241 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules from
+/root/reference (with the import shims of ref_shims.py) on the deterministic cases of
+tests/cases.py.  Runs only in the authoring container; the fixtures are committed and the
+GPU box never needs /root/reference.
+
+    python tests/golden/make_golden.py            # all cases
+    python tests/golden/make_golden.py pretrain   # one case
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import ref_shims  # noqa: E402
+import cases  # noqa: E402
+
+R = ref_shims.load()
+REF_CFG = "/root/reference/config/uc2-base.json"
+
+
+def grad_digest(t):
+    """[L2 norm, 48 strided samples] of a gradient tensor."""
+    f = t.detach().reshape(-1).double()
+    idx = torch.linspace(0, f.numel() - 1, 48).long()
+    return np.concatenate([[f.norm().item()], f[idx].numpy()]).astype(np.float64)
+
+
+def ref_config(cfg, family):
+    C = R.model.VLXLMRConfig if family == "vlxlmr" else R.model.UniterConfig
+    c = C.from_json_file(REF_CFG)
+    c.__dict__.update(cfg.to_dict())
+    return c
+
+
+def build(kind, cfg, family, sd):
+    rc = ref_config(cfg, family)
+    if kind == "pretrain":
+        M = R.model.VLXLMRForPretraining if family == "vlxlmr" else R.model.UniterForPretraining
+        m = M(rc, 2048, 1601)
+    else:
+        M = R.itm.VLXLMRForImageTextRetrieval if family == "vlxlmr" else R.itm.UniterForImageTextRetrieval
+        m = M(rc, 2048, margin=0.2)
+    missing, unexpected = m.load_state_dict(cases.with_aliases(sd, kind, family), strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith("vis_cls.") for k in missing), missing
+    m.eval()   # dropout off (parity runs use p=0, utils/misc.py:54-60)
+    return m
+
+
+def named_unique(m):
+    return [(n, p) for n, p in m.named_parameters() if not n.startswith("vis_cls.")]
+
+
+def run_task(m, batch, task, out, tag, lam=0.1):
+    m.zero_grad(set_to_none=True)
+    res = m(batch, task=task, compute_loss=True)
+    if task == "itm":
+        itm, (pos, neg) = res
+        out[f"{tag}|itm_loss"] = cases.to_np(itm)
+        out[f"{tag}|ot_pos"] = cases.to_np(pos)
+        out[f"{tag}|ot_neg"] = cases.to_np(neg)
+        loss = itm.mean() + lam * (pos.sum() - neg.sum()) / (pos.size(0) + neg.size(0))   # pretrain.py:528-544
+    else:
+        out[f"{tag}|loss_vec"] = cases.to_np(res)
+        loss = res.mean()
+    out[f"{tag}|loss"] = np.array([loss.item()])
+    loss.backward()
+    for n, p in named_unique(m):
+        if p.grad is not None:
+            out[f"{tag}|grad|{n}"] = grad_digest(p.grad)
+    with torch.no_grad():
+        sc = m(batch, task=task, compute_loss=False)
+        sc = sc[0] if task == "itm" else sc
+        s = cases.to_np(sc)
+        out[f"{tag}|scores"] = s if s.shape[-1] <= 2048 else s[:, ::97]
+
+
+def hidden_dump(enc, fam, batch, out, tag, img_masks=None):
+    with torch.no_grad():
+        pos = batch["position_ids"] if fam == "uniter" else None
+        emb = enc._compute_img_txt_embeddings(batch["input_ids"], pos, batch["img_feat"],
+                                              batch["img_pos_feat"], batch["gather_index"], img_masks)
+        layers = enc(batch["input_ids"], pos, batch["img_feat"], batch["img_pos_feat"],
+                     batch["attn_masks"], batch["gather_index"], img_masks=img_masks,
+                     output_all_encoded_layers=True)
+    rows = cases.sample_rows(emb.size(1))
+    out[f"{tag}|emb"] = cases.to_np(emb)            # full packed embedding (checks packing row by row)
+    out[f"{tag}|hidden_rows"] = np.array(rows)
+    out[f"{tag}|hidden"] = np.stack([cases.to_np(h[:, rows]) for h in layers])
+
+
+def case_pretrain(family="vlxlmr"):
+    cfg = cases.config(2, family=family)
+    sd = cases.weights(cfg, "pretrain", family)
+    m = build("pretrain", cfg, family, sd)
+    enc = m.roberta if family == "vlxlmr" else m.bert
+    out = {}
+    b_itm = cases.batch_itm(family=family)
+    hidden_dump(enc, family, b_itm, out, "itm")
+    run_task(m, b_itm, "itm", out, "itm")
+    run_task(m, cases.batch_mlm(family=family), "mlm", out, "mlm")
+    b_mrfr = cases.batch_mrfr(family=family)
+    hidden_dump(enc, family, b_mrfr, out, "mrfr", img_masks=b_mrfr["img_masks"])
+    run_task(m, b_mrfr, "mrfr", out, "mrfr")
+    b_mrc = cases.batch_mrc(family=family)
+    run_task(m, b_mrc, "mrc-kl", out, "mrc-kl")
+    run_task(m, b_mrc, "mrc", out, "mrc")
+    return out
+
+
+def case_rank(family="vlxlmr"):
+    cfg = cases.config(2, family=family)
+    sd = cases.weights(cfg, "retrieval", family)
+    m = build("retrieval", cfg, family, sd)
+    out = {}
+    b = cases.batch_rank(family=family)
+    m.zero_grad(set_to_none=True)
+    loss = m(b, compute_loss=True)
+    out["rank|loss_mat"] = cases.to_np(loss)
+    loss.mean().backward()
+    for n, p in named_unique(m):
+        if p.grad is not None:
+            out[f"rank|grad|{n}"] = grad_digest(p.grad)
+    with torch.no_grad():
+        out["rank|scores"] = cases.to_np(m(b, compute_loss=False))
+    return out
+
+
+def case_cfg1():
+    """BASELINE.json configs[0]: uc2-base 12L, XLM-R vocab, B=8 x (40 tok + 36 regions), ITM forward."""
+    cfg = cases.config(12, vocab=250002)
+    sd = cases.weights(cfg, "retrieval")
+    m = build("retrieval", cfg, "vlxlmr", sd)
+    b = cases.batch_rank(n=8, sample_size=1, seed=42, vocab=250002, txt_len=40, num_bb=36)
+    out = {}
+    hidden_dump(m.roberta, "vlxlmr", b, out, "cfg1")
+    out["cfg1|emb"] = out["cfg1|emb"][:, cases.sample_rows(76)]
+    with torch.no_grad():
+        out["cfg1|scores"] = cases.to_np(m(b, compute_loss=False))
+    return out
+
+
+def case_index():
+    """Integer builders of the reference collates + position ids, on ragged lengths."""
+    out = {}
+    tls = [5, 17, 9, 30, 12, 8]
+    nbs = [10, 36, 100, 11, 40, 23]
+    T, S = max(tls), max(t + n for t, n in zip(tls, nbs))
+    out["gather_index"] = R.data.get_gather_index(tls, nbs, len(tls), T, S).numpy()
+    out["ot_scatter"] = R.data_itm._compute_ot_scatter(tls, T, S).numpy()
+    out["txt_pad"] = R.data_itm._compute_pad(tls, T).numpy()
+    out["img_pad"] = R.data_itm._compute_pad(nbs, max(nbs)).numpy()
+    out["lens"] = np.array([tls, nbs])
+    ids = cases.batch_mlm()["input_ids"]
+    ids[2, 3] = 1      # a pad in the middle: positions skip it (model.py:288-290)
+    out["pos_in"] = ids.numpy()
+    out["pos_out"] = R.model.create_position_ids_from_input_ids(ids, 1).numpy()
+    feats = [torch.arange(n * 3, dtype=torch.float32).view(n, 3) + i for i, n in enumerate(nbs)]
+    out["pad_tensors"] = R.data.pad_tensors(feats, nbs).numpy()
+    return out
+
+
+def case_ot():
+    out = {}
+    b, m_, n_ = 4, 12, 20
+    txt = torch.from_numpy(cases.synth.det_normal((b, m_, 768), 901))
+    img = torch.from_numpy(cases.synth.det_normal((b, n_, 768), 902))
+    tls, nbs = [12, 5, 9, 1], [20, 7, 13, 20]
+    txt_pad = cases.B.compute_pad(tls, m_)
+    img_pad = cases.B.compute_pad(nbs, n_)
+    txt.requires_grad_(True)
+    img.requires_grad_(True)
+    d = R.ot.optimal_transport_dist(txt, img, txt_pad, img_pad)
+    d.sum().backward()
+    out["dist"] = cases.to_np(d)
+    out["dtxt"] = cases.to_np(txt.grad)
+    out["dimg"] = cases.to_np(img.grad)
+    out["lens"] = np.array([tls, nbs])
+    return out
+
+
+def case_adamw():
+    """optim/adamw.py + optim/misc.py grouping + clip_grad_norm_ (pretrain.py:610), 4 steps."""
+    out = {}
+    names = ["enc.dense.weight", "enc.dense.bias", "enc.LayerNorm.weight", "img_layer_norm.weight"]
+    shapes = [(33, 17), (17,), (17,), (17,)]
+
+    class Mod(torch.nn.Module):
+        pass
+    mod = Mod()
+    for i, (n, s) in enumerate(zip(names, shapes)):
+        mod.register_parameter(n.replace(".", "_DOT_"), torch.nn.Parameter(
+            torch.from_numpy(cases.synth.det_normal(s, 700 + i, 0.5))))
+    plist = [(n.replace("_DOT_", "."), p) for n, p in mod.named_parameters()]
+    mod.named_parameters = lambda: plist
+
+    class Opts:
+        weight_decay, optim, learning_rate, betas = 0.01, "adamw", 3e-3, (0.9, 0.98)
+    opt = R.misc.build_optimizer(mod, Opts)
+    out["decay_flags"] = np.array([len(g["params"]) for g in opt.param_groups])
+    import warnings
+    warnings.simplefilter("ignore")
+    for step in range(1, 5):
+        lr = Opts.learning_rate * R.sched.warmup_linear(step, 2, 10)
+        for g in opt.param_groups:
+            g["lr"] = lr
+        for i, (n, p) in enumerate(mod.named_parameters()):
+            p.grad = torch.from_numpy(cases.synth.det_normal(p.shape, 800 + 10 * step + i, 2.0))
+        gn = torch.nn.utils.clip_grad_norm_([p for _, p in plist], 5.0)
+        out[f"gnorm{step}"] = np.array([float(gn)])
+        opt.step()
+        for n, p in mod.named_parameters():
+            out[f"p{step}|{n}"] = cases.to_np(p)
+    return out
+
+
+CASES = {
+    "pretrain": lambda: case_pretrain("vlxlmr"),
+    "pretrain_uniter": lambda: case_pretrain("uniter"),
+    "rank": lambda: case_rank("vlxlmr"),
+    "cfg1": case_cfg1,
+    "index": case_index,
+    "ot": case_ot,
+    "adamw": case_adamw,
+}
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or list(CASES)
+    for name in which:
+        res = CASES[name]()
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **res)
+        print(f"{name}: {len(res)} arrays -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
