@@ -51,7 +51,7 @@ UC2_API long long uc2_launch_count(void);
  *   if act == UC2_ACT_GELU : acc = gelu_erf(acc)          (model/layer.py:31-37)
  *   if act == UC2_ACT_DGELU: acc *= gelu_erf'(aux[m,n])   (backward of the above; aux = pre-act)
  *   if act == UC2_ACT_TANH : acc = tanh(acc)              (model/layer.py:184)
- *   acc += residual[m,n] (bf16)                 -- BertSelfOutput / BertOutput residual
+ *   acc += residual[m,n] (bf16, or fp32 when residual_f32) -- BertSelfOutput / BertOutput residual
  *   out_bf16[m,n] = bf16(acc)  and/or  out_f32[m,n] (= or +=, see accumulate) acc
  * split_k > 1 splits K over CTAs and atomically accumulates into out_f32 (requires accumulate=1,
  * out_f32 only, no bias/act/residual): the wgrad path, which also gives gradient accumulation.
@@ -75,9 +75,220 @@ typedef struct {
     int accumulate;   /* out_f32 += acc (atomic) instead of = */
     int split_k;      /* >= 1 */
     int block_n;      /* 0 = auto; else 64, 128 or 256 */
+    int residual_f32; /* residual points at fp32 (the fp32 residual stream of the encoder) instead of bf16 */
 } uc2_gemm_args;
 
 UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Embeddings fused with the gather_index pack.
+ * Replaces {VLXLMR,Uniter}TextEmbeddings.forward (model/model.py:304-335, 987-1001),
+ * create_position_ids_from_input_ids (280-290), {VLXLMR,Uniter}ImageEmbeddings.forward
+ * (352-364, 1017-1028; the img_linear GEMM itself goes through uc2_gemm_bf16) and the
+ * cat+gather of _compute_img_txt_embeddings (412-425), plus their backward.
+ * All parameter tensors are the fp32 masters.  Output rows: out[b, j] for j < S.
+ *   mode 0: joint, out[b,j] = cat(txt,img)[b, gather_index[b,j]]
+ *   mode 1: text only (S == T);  mode 2: image only (S == R)
+ * position_ids == NULL derives positions from input_ids (VLXLMR); position_rows is 1 (broadcast
+ * [1,T]) or B.  word_pad_id is the token treated as padding for derived positions AND the
+ * word-embedding row that never receives gradient; pos_pad_id likewise for the position table
+ * (-1: none).
+ */
+typedef struct {
+    int B, T, R, S, mode, hidden;
+    const long long* input_ids;
+    const long long* position_ids; int position_rows;
+    const long long* gather_index;
+    int word_pad_id, pos_pad_id;
+    const float* word_emb; const float* pos_emb; const float* type_emb;
+    const float* ln_w; const float* ln_b;
+    const float* y_img;          /* [B*R, 768] fp32: img_linear(img_feat (+mask emb)) incl. bias */
+    const float* img_pos_feat;   /* [B*R, 7] */
+    const float* img_ln_w; const float* img_ln_b;
+    const float* pos_w; const float* pos_b;
+    const float* pos_ln_w; const float* pos_ln_b;
+    const float* fin_ln_w; const float* fin_ln_b;
+    float eps;
+    int vocab, max_pos;
+} uc2_embed_args;
+
+typedef struct {                 /* fp32 gradient accumulators (+=), same shapes as the parameters */
+    float* word_emb; float* pos_emb; float* type_emb;
+    float* ln_w; float* ln_b;
+    float* img_ln_w; float* img_ln_b;
+    float* pos_w; float* pos_b;
+    float* pos_ln_w; float* pos_ln_b;
+    float* fin_ln_w; float* fin_ln_b;
+    float* dy_img;               /* [B*R, 768] fp32 scratch, zeroed by the caller: d(img_linear out) */
+} uc2_embed_grads;
+
+/* img_feat fp32 [rows, dim] (+ mask_embedding.weight[1] where img_masks[row] != 0) -> bf16 */
+UC2_API int uc2_img_prep(const float* img_feat, const unsigned char* img_masks, const float* mask_row1,
+                         void* out_bf16, long long rows, int dim, void* stream);
+/* out_bf16 [B*S,768] (tensor-core operand) and, optionally, out_f32 (start of the fp32 residual stream) */
+UC2_API int uc2_embed_pack_fwd(const uc2_embed_args* a, void* out_bf16, float* out_f32, void* stream);
+UC2_API int uc2_embed_pack_bwd(const uc2_embed_args* a, const void* dout_bf16, const uc2_embed_grads* g,
+                               void* stream);
+/* dy_img fp32 -> bf16 copy (wgrad operand), dbias += column sums, masked_sum += sum of masked rows */
+UC2_API int uc2_img_grad_finish(const float* dy_img, const unsigned char* img_masks, void* dy_bf16, float* dbias,
+                                float* masked_sum, long long rows, void* stream);
+/* out[n] += sum_k v[k] W[k,n]  (d mask_embedding.weight[1] = masked_sum @ img_linear.weight) */
+UC2_API int uc2_vecmat_acc(const float* v, const float* W, float* out, int K, int N, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over rows of 768 (apex FusedLayerNorm call sites model/layer.py:108,149 and the
+ * head transforms), forward and backward.  x/y/dy/dx are bf16 [rows, 768]; gamma/beta fp32.
+ * Backward accumulates dgamma/dbeta (+=) and, if dbias != NULL, the column sums of dx (the bias
+ * gradient of the Linear that produced x).
+ */
+/* x is bf16, or fp32 when x_is_f32 (the encoder's fp32 residual stream); y_bf16 and/or y_f32 are written. */
+UC2_API int uc2_layernorm_fwd(const void* x, int x_is_f32, const float* gamma, const float* beta, float eps,
+                              void* y_bf16, float* y_f32, long long rows, void* stream);
+UC2_API int uc2_layernorm_bwd(const void* x, int x_is_f32, const void* dy, const float* gamma, float eps, void* dx,
+                              float* dgamma, float* dbeta, float* dbias, long long rows, void* stream);
+/* out[c] += sum_r x[r, c] for bf16 x [rows, cols] with leading dimension ld (bias gradients) */
+UC2_API int uc2_colsum_bf16(const void* x, long long ld, long long rows, int cols, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Key-padding-masked multi-head self-attention, flash style (no [B,12,S,S] tensor).
+ * Replaces BertSelfAttention.forward model/layer.py:80-100 after the QKV projection.
+ * qkv: bf16 [B*S, 2304] = [q | k | v], heads of 64 inside each third.  attn_mask: int64 [B,S]
+ * of {0,1}; the additive mask is (1-m)*-10000 exactly as model/model.py:433-436.
+ * ctx: bf16 [B*S, 768] (heads merged, i.e. the permute+view of layer.py:98-100 is free).
+ * lse: fp32 [B,12,S] log-sum-exp saved for backward.
+ */
+UC2_API int uc2_attention_fwd(const void* qkv, const long long* attn_mask, void* ctx, float* lse, int B, int S,
+                              void* stream);
+/* dqkv: bf16 [B*S, 2304] (fully overwritten). delta_ws: fp32 [B,12,S] scratch. */
+UC2_API int uc2_attention_bwd(const void* qkv, const long long* attn_mask, const void* ctx, const void* dctx,
+                              const float* lse, float* delta_ws, void* dqkv, int B, int S, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The BertLayer stack: BertLayer.forward model/layer.py:159-170 applied num_hidden_layers times
+ * ({VLXLMR,Uniter}Encoder.forward model/model.py:373-383 / 1038-1048) and its backward.
+ * The arrays w / acts / grads are HOST arrays of n_layers structs holding DEVICE pointers.
+ * Weights are the bf16 shadows ([out,in] row-major, Q/K/V concatenated along `out`), biases and
+ * LayerNorm parameters the fp32 masters.  Activations are bf16 except lse (fp32 [B,12,S]).
+ * For inference (save_for_bwd == 0) every layer may point at the same activation buffers and
+ * `u` may be NULL.
+ */
+typedef struct {
+    const void* w_qkv; const float* b_qkv;      /* [2304,768], [2304] */
+    const void* w_o; const float* b_o;          /* attention.output.dense */
+    const float* ln1_w; const float* ln1_b;     /* attention.output.LayerNorm (eps 1e-12) */
+    const void* w_ffn1; const float* b_ffn1;    /* intermediate.dense [3072,768] */
+    const void* w_ffn2; const float* b_ffn2;    /* output.dense [768,3072] */
+    const float* ln2_w; const float* ln2_b;     /* output.LayerNorm (eps 1e-12) */
+} uc2_layer_weights;
+
+typedef struct {                                /* fp32 accumulators (+=), shapes as above */
+    float* w_qkv; float* b_qkv; float* w_o; float* b_o; float* ln1_w; float* ln1_b;
+    float* w_ffn1; float* b_ffn1; float* w_ffn2; float* b_ffn2; float* ln2_w; float* ln2_b;
+} uc2_layer_grads;
+
+typedef struct {
+    void* qkv;    /* [M,2304] */
+    void* ctx;    /* [M,768]  attention output, heads merged */
+    float* lse;   /* [B,12,S] */
+    void* z1;     /* [M,768]  fp32: O-proj + bias + residual (LayerNorm input) */
+    void* h1;     /* [M,768]  attention block output */
+    void* u;      /* [M,3072] FFN1 pre-activation */
+    void* g;      /* [M,3072] gelu(u) */
+    void* z2;     /* [M,768]  fp32: FFN2 + bias + residual */
+    void* out;    /* [M,768]  layer output */
+} uc2_layer_acts;
+
+/* x_in: bf16 [M,768] embedding output; x_in_f32: the same rows in fp32 (start of the residual stream).
+ * workspace: uc2_encoder_fwd_workspace_bytes(B,S) bytes, 256-byte aligned (rotating fp32 residual buffers). */
+UC2_API size_t uc2_encoder_fwd_workspace_bytes(int B, int S);
+UC2_API int uc2_encoder_fwd(const void* x_in, const float* x_in_f32, const long long* attn_mask, int B, int S,
+                            int n_layers, const uc2_layer_weights* w, const uc2_layer_acts* acts, int save_for_bwd,
+                            void* workspace, size_t workspace_bytes, void* stream);
+UC2_API size_t uc2_encoder_bwd_workspace_bytes(int B, int S);
+/* dout: bf16 [M,768] gradient of the last layer's output; dx_in: bf16 [M,768] gradient of x_in (written). */
+UC2_API int uc2_encoder_bwd(const void* x_in, const long long* attn_mask, int B, int S, int n_layers,
+                            const uc2_layer_weights* w, const uc2_layer_acts* acts, const uc2_layer_grads* grads,
+                            const void* dout, void* dx_in, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Heads and losses (warp-level kernels).
+ */
+/* Narrow Linear (N <= 8): itm_output Linear(768,2) model/model.py:476,698; rank_output Linear(768,1)
+ * model/itm.py:19,42.  x fp32 [M,K] (row pitch ldx), W fp32 [N,K]; out fp32 [M,N]. */
+UC2_API int uc2_narrow_linear_fwd(const float* x, long long ldx, const float* W, const float* b, float* out, int M,
+                                  int N, int K, void* stream);
+/* dx (fp32, row pitch lddx, may be NULL) = dy W;  dW += dy^T x;  db += colsum(dy) */
+UC2_API int uc2_narrow_linear_bwd(const float* x, long long ldx, const float* W, const float* dy, float* dx,
+                                  long long lddx, float* dW, float* db, int M, int N, int K, void* stream);
+/* BertPooler tanh backward (model/layer.py:184): dpre = dy * (1 - y^2), written as bf16 */
+UC2_API int uc2_tanh_bwd(const float* y, const float* dy, void* dpre_bf16, long long n, void* stream);
+/* Triplet ranking loss, model/itm.py:43-53: scores [groups*sample_size] -> loss [groups, sample_size-1] */
+UC2_API int uc2_rank_loss_fwd(const float* scores, float* loss, int groups, int sample_size, float margin, void* stream);
+UC2_API int uc2_rank_loss_bwd(const float* scores, const float* dloss, float* dscores, int groups, int sample_size,
+                              float margin, void* stream);
+/* Row-wise log-softmax losses over fp32 logits [rows, C] (pitch ld), reduction 'none':
+ *   kind 0: F.cross_entropy with int64 targets (model/model.py:593-595, 732, 770-772; ignore_index or -1)
+ *   kind 1: F.kl_div(log_softmax(x), soft_targets) elementwise [rows, C] (model/model.py:763-766)
+ * loss / dlogits / lse_out are optional outputs; dlogits needs dloss (same shape as loss). */
+UC2_API int uc2_softmax_loss(const float* logits, long long ld, long long rows, int C, int kind,
+                             const long long* targets, long long ignore_index, const float* soft_targets, float* loss,
+                             const float* dloss, float* dlogits, float* lse_out, void* stream);
+/* F.mse_loss(reduction='none') model/model.py:684-685 and its backward */
+UC2_API int uc2_mse(const float* pred, const float* tgt, float* loss, const float* dloss, float* dpred, long long n,
+                    void* stream);
+/* Order-exact masked-row compaction, _compute_masked_hidden model/model.py:653-657, without a host sync.
+ * mask: bytes [B*mask_L] row-major; index[i] = flat position of the i-th set byte; *count = number set. */
+UC2_API int uc2_mask_scan(const unsigned char* mask, long long n, int* index, int* count, int capacity, void* stream);
+/* out[i,:] = src[(index[i] / mask_L) * src_S + index[i] % mask_L, :] for i < min(*count, capacity); rows of 768 bf16 */
+UC2_API int uc2_gather_rows(const void* src, const int* index, const int* count, int mask_L, int src_S, void* out,
+                            int capacity, void* stream);
+UC2_API int uc2_scatter_rows_add(const void* dout, const int* index, const int* count, int mask_L, int src_S,
+                                 void* dsrc, int capacity, void* stream);
+/* dz = dy * gelu_erf'(pre), bf16 elementwise (backward of the head transforms, model/layer.py:258-260) */
+UC2_API int uc2_dgelu_bf16(const void* dy, const void* pre, void* out, long long n, void* stream);
+UC2_API int uc2_f32_to_bf16_2d(const float* x, long long ldx, void* y, long long ldy, long long rows, int cols,
+                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * WRA optimal transport: optimal_transport_dist model/ot.py:66-82 (cost_matrix_cosine 8-18, ipot
+ * 32-63, trace 21-29) fused with the scatter un-pack of forward_itm model/model.py:703-716.
+ * seq: bf16 [B,S,768] packed encoder output; ot_scatter: int64 [B,S] context position of each packed
+ * row; text rows are context positions [0,M), image rows [tl, tl+N) with tl = input_ids.size(1);
+ * txt_pad [B,M] / img_pad [B,N]: bytes, 1 = padding.  dist: fp32 [B].  C_save [B,N,M] / T_save
+ * [B,N,M] fp32 are saved for backward.  Backward writes d(dist)/d(seq) (T detached, as ot.py:79-81)
+ * into dseq (bf16 [B,S,768], zero-initialised by the caller).  Limits: M, N <= 128.
+ */
+UC2_API int uc2_ot_ipot_fwd(const void* seq, const long long* ot_scatter, const unsigned char* txt_pad,
+                            const unsigned char* img_pad, int B, int S, int M, int N, int tl, float beta,
+                            int iterations, int k, float* dist, float* C_save, float* T_save, void* stream);
+UC2_API int uc2_ot_ipot_bwd(const void* seq, const long long* ot_scatter, const unsigned char* txt_pad,
+                            const unsigned char* img_pad, int B, int S, int M, int N, int tl, const float* C_save,
+                            const float* T_save, const float* ddist, void* dseq, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser on flat arenas: optim/adamw.py:40-103 (AdamW.step), pretrain.py:610 (clip_grad_norm_),
+ * optimizer.zero_grad(), and the fp32 -> bf16 weight shadow refresh (replaces apex amp O2 master
+ * weights, pretrain.py:463-465).  A "chunk" is a <= 8192-element slice of one parameter tensor.
+ */
+typedef struct { long long offset; int n; int tensor; } uc2_opt_chunk;
+typedef struct {
+    float lr[8]; float weight_decay[8];   /* per param group */
+    float beta1, beta2, eps;
+    int correct_bias;
+    int global_step;                      /* 1-based count of optimizer steps */
+    float max_grad_norm;                  /* <= 0: no clipping */
+    int zero_grad;                        /* also clear the gradient arena */
+} uc2_adamw_hyper;
+
+UC2_API int uc2_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+/* *out (double, device) = sum of squares of the gradients of tensors with act_step >= 0 */
+UC2_API int uc2_grad_sqnorm(const float* grad, const uc2_opt_chunk* chunks, int n_chunks, const int* act_step,
+                            double* out, void* stream);
+/* act_step[t]: global step at which tensor t first had a gradient (-1: never -> skipped, as p.grad is None);
+ * group_of[t]: param group; sqnorm: device scalar from uc2_grad_sqnorm (may be NULL when not clipping). */
+UC2_API int uc2_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                           const uc2_opt_chunk* chunks, int n_chunks, const int* act_step, const int* group_of,
+                           const uc2_adamw_hyper* hyper, const double* sqnorm, void* stream);
 
 #ifdef __cplusplus
 }

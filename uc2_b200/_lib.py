@@ -13,22 +13,93 @@ LIB_PATH = os.path.join(_HERE, "libuc2_b200.so")
 _lib = None
 
 ACT_NONE, ACT_GELU, ACT_DGELU, ACT_TANH = 0, 1, 2, 3
+P, LL, I, F, SZ = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_size_t
 
 
 class GemmArgs(C.Structure):
-    _fields_ = [
-        ("a", C.c_void_p), ("lda", C.c_longlong), ("a_mn", C.c_int),
-        ("b", C.c_void_p), ("ldb", C.c_longlong), ("b_mn", C.c_int),
-        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-        ("bias", C.c_void_p),
-        ("residual", C.c_void_p), ("ld_res", C.c_longlong),
-        ("aux", C.c_void_p), ("ld_aux", C.c_longlong),
-        ("act", C.c_int),
-        ("out_bf16", C.c_void_p), ("ld_out", C.c_longlong),
-        ("out_pre", C.c_void_p), ("ld_pre", C.c_longlong),
-        ("out_f32", C.c_void_p), ("ld_f32", C.c_longlong),
-        ("accumulate", C.c_int), ("split_k", C.c_int), ("block_n", C.c_int),
-    ]
+    _fields_ = [("a", P), ("lda", LL), ("a_mn", I), ("b", P), ("ldb", LL), ("b_mn", I),
+                ("M", I), ("N", I), ("K", I), ("bias", P), ("residual", P), ("ld_res", LL),
+                ("aux", P), ("ld_aux", LL), ("act", I), ("out_bf16", P), ("ld_out", LL),
+                ("out_pre", P), ("ld_pre", LL), ("out_f32", P), ("ld_f32", LL),
+                ("accumulate", I), ("split_k", I), ("block_n", I), ("residual_f32", I)]
+
+
+class EmbedArgs(C.Structure):
+    _fields_ = [("B", I), ("T", I), ("R", I), ("S", I), ("mode", I), ("hidden", I),
+                ("input_ids", P), ("position_ids", P), ("position_rows", I), ("gather_index", P),
+                ("word_pad_id", I), ("pos_pad_id", I),
+                ("word_emb", P), ("pos_emb", P), ("type_emb", P), ("ln_w", P), ("ln_b", P),
+                ("y_img", P), ("img_pos_feat", P), ("img_ln_w", P), ("img_ln_b", P),
+                ("pos_w", P), ("pos_b", P), ("pos_ln_w", P), ("pos_ln_b", P),
+                ("fin_ln_w", P), ("fin_ln_b", P), ("eps", F), ("vocab", I), ("max_pos", I)]
+
+
+class EmbedGrads(C.Structure):
+    _fields_ = [(n, P) for n in ("word_emb", "pos_emb", "type_emb", "ln_w", "ln_b", "img_ln_w", "img_ln_b",
+                                 "pos_w", "pos_b", "pos_ln_w", "pos_ln_b", "fin_ln_w", "fin_ln_b", "dy_img")]
+
+
+LAYER_FIELDS = ("w_qkv", "b_qkv", "w_o", "b_o", "ln1_w", "ln1_b", "w_ffn1", "b_ffn1", "w_ffn2", "b_ffn2",
+                "ln2_w", "ln2_b")
+ACT_FIELDS = ("qkv", "ctx", "lse", "z1", "h1", "u", "g", "z2", "out")
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, P) for n in LAYER_FIELDS]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [(n, P) for n in LAYER_FIELDS]
+
+
+class LayerActs(C.Structure):
+    _fields_ = [(n, P) for n in ACT_FIELDS]
+
+
+class OptChunk(C.Structure):
+    _fields_ = [("offset", LL), ("n", I), ("tensor", I)]
+
+
+class AdamwHyper(C.Structure):
+    _fields_ = [("lr", F * 8), ("weight_decay", F * 8), ("beta1", F), ("beta2", F), ("eps", F),
+                ("correct_bias", I), ("global_step", I), ("max_grad_norm", F), ("zero_grad", I)]
+
+
+_SIGS = {
+    "uc2_gemm_bf16": [C.POINTER(GemmArgs), P],
+    "uc2_img_prep": [P, P, P, P, LL, I, P],
+    "uc2_embed_pack_fwd": [C.POINTER(EmbedArgs), P, P, P],
+    "uc2_embed_pack_bwd": [C.POINTER(EmbedArgs), P, C.POINTER(EmbedGrads), P],
+    "uc2_img_grad_finish": [P, P, P, P, P, LL, P],
+    "uc2_vecmat_acc": [P, P, P, I, I, P],
+    "uc2_layernorm_fwd": [P, I, P, P, F, P, P, LL, P],
+    "uc2_layernorm_bwd": [P, I, P, P, F, P, P, P, P, LL, P],
+    "uc2_colsum_bf16": [P, LL, LL, I, P, P],
+    "uc2_attention_fwd": [P, P, P, P, I, I, P],
+    "uc2_attention_bwd": [P, P, P, P, P, P, P, I, I, P],
+    "uc2_encoder_fwd": [P, P, P, I, I, I, C.POINTER(LayerWeights), C.POINTER(LayerActs), I, P, SZ, P],
+    "uc2_encoder_bwd": [P, P, I, I, I, C.POINTER(LayerWeights), C.POINTER(LayerActs), C.POINTER(LayerGrads),
+                        P, P, P, SZ, P],
+    "uc2_narrow_linear_fwd": [P, LL, P, P, P, I, I, I, P],
+    "uc2_narrow_linear_bwd": [P, LL, P, P, P, LL, P, P, I, I, I, P],
+    "uc2_tanh_bwd": [P, P, P, LL, P],
+    "uc2_rank_loss_fwd": [P, P, I, I, F, P],
+    "uc2_rank_loss_bwd": [P, P, P, I, I, F, P],
+    "uc2_softmax_loss": [P, LL, LL, I, I, P, LL, P, P, P, P, P, P],
+    "uc2_mse": [P, P, P, P, P, LL, P],
+    "uc2_mask_scan": [P, LL, P, P, I, P],
+    "uc2_gather_rows": [P, P, P, I, I, P, I, P],
+    "uc2_scatter_rows_add": [P, P, P, I, I, P, I, P],
+    "uc2_dgelu_bf16": [P, P, P, LL, P],
+    "uc2_f32_to_bf16_2d": [P, LL, P, LL, LL, I, P],
+    "uc2_ot_ipot_fwd": [P, P, P, P, I, I, I, I, I, F, I, I, P, P, P, P],
+    "uc2_ot_ipot_bwd": [P, P, P, P, I, I, I, I, I, P, P, P, P, P],
+    "uc2_cast_f32_bf16": [P, P, LL, P],
+    "uc2_grad_sqnorm": [P, P, I, P, P, P],
+    "uc2_adamw_step": [P, P, P, P, P, P, I, P, P, C.POINTER(AdamwHyper), P, P],
+}
+EXPORTS = sorted(list(_SIGS) + ["uc2_last_error", "uc2_version", "uc2_launch_count",
+                                "uc2_encoder_bwd_workspace_bytes", "uc2_encoder_fwd_workspace_bytes"])
 
 
 def lib():
@@ -38,9 +109,18 @@ def lib():
             raise RuntimeError(
                 f"uc2_b200: {LIB_PATH} not found. Build it with `python -m uc2_b200.build` "
                 "(there is no CPU / PyTorch fallback for this path).")
-        _lib = C.CDLL(LIB_PATH)
-        _lib.uc2_last_error.restype = C.c_char_p
-        _lib.uc2_launch_count.restype = C.c_longlong
+        L = C.CDLL(LIB_PATH)
+        L.uc2_last_error.restype = C.c_char_p
+        L.uc2_launch_count.restype = C.c_longlong
+        L.uc2_encoder_bwd_workspace_bytes.restype = SZ
+        L.uc2_encoder_bwd_workspace_bytes.argtypes = [I, I]
+        L.uc2_encoder_fwd_workspace_bytes.restype = SZ
+        L.uc2_encoder_fwd_workspace_bytes.argtypes = [I, I]
+        for name, sig in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = sig
+            fn.restype = I
+        _lib = L
     return _lib
 
 
@@ -50,12 +130,16 @@ def check(rc, what=""):
         raise RuntimeError(f"uc2_b200 {what} failed (code {rc}): {msg}")
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream():
+    return torch.cuda.current_stream().cuda_stream
 
 
 def ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)
 
 
 def launch_count():
@@ -63,7 +147,8 @@ def launch_count():
 
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None, residual=None, aux=None,
-         act=ACT_NONE, out_bf16=None, out_pre=None, out_f32=None, accumulate=False, split_k=1, block_n=0):
+         act=ACT_NONE, out_bf16=None, out_pre=None, out_f32=None, accumulate=False, split_k=1, block_n=0,
+         ld_out=None, ld_res=None):
     """D[M,N] = A[M,K] @ B[N,K]^T with the fused epilogue described in include/uc2_b200.h."""
     g = GemmArgs()
     g.a, g.lda, g.a_mn = a.data_ptr(), (lda if lda is not None else a.stride(0)), int(a_mn)
@@ -71,15 +156,16 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None
     g.M, g.N, g.K = M, N, K
     g.bias = bias.data_ptr() if bias is not None else None
     if residual is not None:
-        g.residual, g.ld_res = residual.data_ptr(), residual.stride(0)
+        g.residual, g.ld_res = residual.data_ptr(), (ld_res if ld_res is not None else residual.stride(0))
+        g.residual_f32 = int(residual.dtype == torch.float32)
     if aux is not None:
         g.aux, g.ld_aux = aux.data_ptr(), aux.stride(0)
     g.act = act
     if out_bf16 is not None:
-        g.out_bf16, g.ld_out = out_bf16.data_ptr(), out_bf16.stride(0)
+        g.out_bf16, g.ld_out = out_bf16.data_ptr(), (ld_out if ld_out is not None else out_bf16.stride(0))
     if out_pre is not None:
         g.out_pre, g.ld_pre = out_pre.data_ptr(), out_pre.stride(0)
     if out_f32 is not None:
         g.out_f32, g.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
     g.accumulate, g.split_k, g.block_n = int(accumulate), split_k, block_n
-    check(lib().uc2_gemm_bf16(C.byref(g), stream_ptr()), "gemm")
+    check(lib().uc2_gemm_bf16(C.byref(g), stream()), "gemm")

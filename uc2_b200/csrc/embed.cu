@@ -124,7 +124,7 @@ __device__ __forceinline__ void pos_linear(const EmbedParams& p, const float* f7
 }
 
 __global__ void __launch_bounds__(EMB_WARPS * 32)
-embed_pack_fwd_kernel(const EmbedParams p, bf16* __restrict__ out) {
+embed_pack_fwd_kernel(const EmbedParams p, bf16* __restrict__ out, float* __restrict__ out32) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * EMB_WARPS + (threadIdx.x >> 5);
     if (row >= (long long)p.B * p.S) return;
@@ -153,6 +153,10 @@ embed_pack_fwd_kernel(const EmbedParams p, bf16* __restrict__ out) {
         ln_apply(v, p.fin_ln_w, p.fin_ln_b, lane, p.eps);
     }
     store_row_bf16(out + row * HID, lane, v);
+    if (out32) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) store8_f32(out32 + row * HID + col_of(lane, i), v + 8 * i);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ backward
@@ -386,14 +390,14 @@ extern "C" UC2_API int uc2_img_prep(const float* img_feat, const unsigned char* 
     return check_last("img_prep_kernel");
 }
 
-extern "C" UC2_API int uc2_embed_pack_fwd(const uc2_embed_args* a, void* out_bf16, void* stream) {
+extern "C" UC2_API int uc2_embed_pack_fwd(const uc2_embed_args* a, void* out_bf16, float* out_f32, void* stream) {
     if (int rc = require_sm100()) return rc;
     UC2_REQUIRE(a && out_bf16, UC2_ERR_ARG, "embed_pack_fwd: null");
     EmbedParams p;
     if (int rc = fill_params(p, *a)) return rc;
     const long long rows = (long long)p.B * p.S;
     embed_pack_fwd_kernel<<<(unsigned)((rows + EMB_WARPS - 1) / EMB_WARPS), EMB_WARPS * 32, 0,
-                            (cudaStream_t)stream>>>(p, (bf16*)out_bf16);
+                            (cudaStream_t)stream>>>(p, (bf16*)out_bf16, out_f32);
     return check_last("embed_pack_fwd_kernel");
 }
 

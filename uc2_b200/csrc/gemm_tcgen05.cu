@@ -40,7 +40,7 @@ struct GemmParams {
     int M, N, K;
     int num_m_blocks, num_n_blocks, split_k, k_blocks_per_split, num_k_blocks;
     const float* bias;
-    const bf16* residual; long long ld_res;
+    const bf16* residual; long long ld_res; int res_f32;
     const bf16* aux; long long ld_aux;
     int act;
     bf16* out_bf16; long long ld_out;
@@ -240,9 +240,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             for (int e = 0; e < 4; ++e) v[e] = apply_act(v[e], p.act, a[e]);
                         }
                         if (p.residual) {
-                            const uint2 u = *reinterpret_cast<const uint2*>(p.residual + grow * p.ld_res + gcol);
-                            const float2 r0 = unpack_bf16(u.x), r1 = unpack_bf16(u.y);
-                            v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+                            if (p.res_f32) {
+                                const float4 r4 = *reinterpret_cast<const float4*>(
+                                    reinterpret_cast<const float*>(p.residual) + grow * p.ld_res + gcol);
+                                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+                            } else {
+                                const uint2 u = *reinterpret_cast<const uint2*>(p.residual + grow * p.ld_res + gcol);
+                                const float2 r0 = unpack_bf16(u.x), r1 = unpack_bf16(u.y);
+                                v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+                            }
                         }
                         if (p.out_bf16) {
                             uint2 o = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
@@ -271,7 +277,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                     p.act == UC2_ACT_DGELU ? __bfloat162float(p.aux[grow * p.ld_aux + gc]) : 0.f;
                                 x = apply_act(x, p.act, a);
                             }
-                            if (p.residual) x += __bfloat162float(p.residual[grow * p.ld_res + gc]);
+                            if (p.residual)
+                                x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[grow * p.ld_res + gc]
+                                               : __bfloat162float(p.residual[grow * p.ld_res + gc]);
                             if (p.out_bf16) p.out_bf16[grow * p.ld_out + gc] = __float2bfloat16(x);
                             if (p.out_f32) {
                                 if (p.accumulate) atomicAdd(p.out_f32 + grow * p.ld_f32 + gc, x);
@@ -401,7 +409,25 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
                 a.ldb);
     UC2_REQUIRE(a.out_bf16 || a.out_f32, UC2_ERR_ARG, "uc2_gemm_bf16: no output");
     UC2_REQUIRE(a.act != UC2_ACT_DGELU || a.aux, UC2_ERR_ARG, "uc2_gemm_bf16: DGELU needs aux");
-    const int split_k = a.split_k < 1 ? 1 : a.split_k;
+    int split_k = a.split_k < 0 ? 1 : a.split_k;
+    if (split_k == 0) {
+        // auto: only meaningful for the atomic-accumulate (wgrad) form; fill the SMs with K splits
+        split_k = 1;
+        const bool can_split = a.out_f32 && a.accumulate && !a.out_bf16 && !a.out_pre && !a.bias && !a.residual &&
+                               a.act == UC2_ACT_NONE;
+        if (can_split) {
+            const int bn0 = a.block_n ? a.block_n : (a.N >= 256 ? 256 : (a.N >= 128 ? 128 : 64));
+            const long long tiles = 1LL * ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + bn0 - 1) / bn0);
+            const int kblocks = (a.K + BLOCK_K - 1) / BLOCK_K;
+            const int sms = num_sms();
+            double best = 0.0;
+            for (int s = 1; s <= 32 && kblocks / s >= 4; ++s) {
+                const long long t = tiles * s;
+                const double eff = (double)t / (double)(((t + sms - 1) / sms) * sms);
+                if (eff > best + 0.03) { best = eff; split_k = s; }
+            }
+        }
+    }
     if (split_k > 1)
         UC2_REQUIRE(a.out_f32 && a.accumulate && !a.out_bf16 && !a.out_pre && !a.bias && !a.residual &&
                         a.act == UC2_ACT_NONE,
@@ -414,7 +440,7 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
     p.k_blocks_per_split = (p.num_k_blocks + p.split_k - 1) / p.split_k;
     p.split_k = (p.num_k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;   // no empty splits
     p.bias = a.bias;
-    p.residual = static_cast<const bf16*>(a.residual); p.ld_res = a.ld_res;
+    p.residual = static_cast<const bf16*>(a.residual); p.ld_res = a.ld_res; p.res_f32 = a.residual_f32;
     p.aux = static_cast<const bf16*>(a.aux); p.ld_aux = a.ld_aux;
     p.act = a.act;
     p.out_bf16 = static_cast<bf16*>(a.out_bf16); p.ld_out = a.ld_out;
@@ -428,7 +454,7 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
                (!a.out_f32 || (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0) &&
                (!a.out_bf16 || (reinterpret_cast<uintptr_t>(a.out_bf16) & 7) == 0) &&
                (!a.out_pre || (reinterpret_cast<uintptr_t>(a.out_pre) & 7) == 0) &&
-               (!a.residual || (reinterpret_cast<uintptr_t>(a.residual) & 7) == 0) &&
+               (!a.residual || (reinterpret_cast<uintptr_t>(a.residual) & (a.residual_f32 ? 15 : 7)) == 0) &&
                (!a.aux || (reinterpret_cast<uintptr_t>(a.aux) & 7) == 0);
     int bn = a.block_n;
     if (bn == 0) bn = pick_block_n(a.M, a.N, p.split_k);

@@ -1,0 +1,204 @@
+// LayerNorm over rows of 768 (fp32 statistics) forward + backward, and a bf16 column-sum (bias gradients).
+// Replaces the apex FusedLayerNorm call sites of model/layer.py:108,149,196,242 and the head transforms
+// in model/model.py:1148,1164.  The input row is bf16 (heads) or fp32 (the encoder keeps its residual
+// stream -- the LayerNorm inputs and outputs -- in fp32 so that rounding does not accumulate across the
+// 12 layers; the bf16 copy of the output is the tensor-core operand of the next GEMM).
+// HBM-bound: one warp per row, 16/32-byte accesses.
+#include "common.cuh"
+
+namespace uc2 {
+namespace {
+
+constexpr int VPL = 24;
+constexpr int LN_WARPS = 8;
+
+__device__ __forceinline__ int col_of(int lane, int i) { return i * 256 + lane * 8; }
+
+template <bool F32>
+__device__ __forceinline__ void load_row(const void* base, long long row, int lane, float* v) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (F32) load8_f32(static_cast<const float*>(base) + row * HID + col_of(lane, i), v + 8 * i);
+        else     load8_bf16(static_cast<const bf16*>(base) + row * HID + col_of(lane, i), v + 8 * i);
+    }
+}
+
+__device__ __forceinline__ void stats(const float* v, float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += v[i];
+    mean = warp_sum(s) * (1.0f / HID);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { const float d = v[i] - mean; q += d * d; }
+    rstd = rsqrtf(warp_sum(q) * (1.0f / HID) + eps);
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float eps, bf16* __restrict__ y, float* __restrict__ y32, long long rows) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[VPL];
+    load_row<F32>(x, row, lane, v);
+    float mean, rstd;
+    stats(v, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float g[8], b[8], o[8];
+        load8_f32(gamma + col_of(lane, i), g);
+        load8_f32(beta + col_of(lane, i), b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * g[k] + b[k];
+        if (y) store8_bf16(y + row * HID + col_of(lane, i), o);
+        if (y32) store8_f32(y32 + row * HID + col_of(lane, i), o);
+    }
+}
+
+// Each warp walks rows with a grid stride and keeps dgamma/dbeta/dbias partial sums in registers;
+// one shared-memory reduction and one global atomic per column per CTA at the end.
+template <bool F32>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ gamma,
+                     float eps, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dbias, long long rows) {
+    __shared__ float red[3 * HID];
+    for (int i = threadIdx.x; i < 3 * HID; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    float g[VPL];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) load8_f32(gamma + col_of(lane, i), g + 8 * i);
+    float ag[VPL], ab[VPL], ax[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) ag[i] = ab[i] = ax[i] = 0.f;
+    for (long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * LN_WARPS) {
+        float v[VPL], d[VPL];
+        load_row<F32>(x, row, lane, v);
+        load_row<false>(dy, row, lane, d);
+        float mean, rstd;
+        stats(v, eps, mean, rstd);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            v[i] = (v[i] - mean) * rstd;          // xhat
+            ag[i] += d[i] * v[i];
+            ab[i] += d[i];
+            d[i] *= g[i];
+            s1 += d[i];
+            s2 += d[i] * v[i];
+        }
+        s1 = warp_sum(s1) * (1.0f / HID);
+        s2 = warp_sum(s2) * (1.0f / HID);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            d[i] = rstd * (d[i] - s1 - v[i] * s2);
+            ax[i] += d[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) store8_bf16(dx + row * HID + col_of(lane, i), d + 8 * i);
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = col_of(lane, i >> 3) + (i & 7);
+        atomicAdd(red + c, ag[i]);
+        atomicAdd(red + HID + c, ab[i]);
+        atomicAdd(red + 2 * HID + c, ax[i]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < HID; c += blockDim.x) {
+        atomicAdd(dgamma + c, red[c]);
+        atomicAdd(dbeta + c, red[HID + c]);
+        if (dbias) atomicAdd(dbias + c, red[2 * HID + c]);
+    }
+}
+
+// column sums of a bf16 matrix: CTA = 8 row phases x 256 columns (8 per thread)
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, long long rows, int cols, float* __restrict__ out,
+                   int row_chunk) {
+    const int cg = blockIdx.x * 256 + (threadIdx.x & 31) * 8;      // 8 consecutive columns per thread
+    const int rsub = threadIdx.x >> 5;                              // 8 row phases
+    const long long r0 = (long long)blockIdx.y * row_chunk;
+    const long long r1 = r0 + row_chunk < rows ? r0 + row_chunk : rows;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (cg + 8 <= cols) {
+        for (long long r = r0 + rsub; r < r1; r += 8) {
+            float v[8];
+            load8_bf16(x + r * ld + cg, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v[k];
+        }
+    } else if (cg < cols) {
+        for (long long r = r0 + rsub; r < r1; r += 8)
+            for (int k = 0; k < 8 && cg + k < cols; ++k) acc[k] += __bfloat162float(x[r * ld + cg + k]);
+    }
+    __shared__ float red[8][256 + 8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[rsub][(threadIdx.x & 31) * 8 + k] = acc[k];
+    __syncthreads();
+    const int c = threadIdx.x;
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][c];
+    const int gc = blockIdx.x * 256 + c;
+    if (gc < cols && s != 0.f) atomicAdd(out + gc, s);
+}
+
+}  // namespace
+}  // namespace uc2
+
+using namespace uc2;
+
+extern "C" UC2_API int uc2_layernorm_fwd(const void* x, int x_is_f32, const float* gamma, const float* beta, float eps,
+                                         void* y_bf16, float* y_f32, long long rows, void* stream) {
+    if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(x && gamma && beta && (y_bf16 || y_f32) && rows > 0, UC2_ERR_ARG, "layernorm_fwd: bad args");
+    UC2_REQUIRE(aligned16(x) && aligned16(y_bf16) && aligned16(y_f32) && aligned16(gamma) && aligned16(beta), UC2_ERR_ARG,
+                "layernorm_fwd: pointers must be 16-byte aligned");
+    const unsigned blocks = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+    if (x_is_f32)
+        layernorm_fwd_kernel<true><<<blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, (bf16*)y_bf16,
+                                                                                      y_f32, rows);
+    else
+        layernorm_fwd_kernel<false><<<blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, (bf16*)y_bf16,
+                                                                                       y_f32, rows);
+    return check_last("layernorm_fwd_kernel");
+}
+
+extern "C" UC2_API int uc2_layernorm_bwd(const void* x, int x_is_f32, const void* dy, const float* gamma, float eps,
+                                         void* dx, float* dgamma, float* dbeta, float* dbias, long long rows,
+                                         void* stream) {
+    if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(x && dy && gamma && dx && dgamma && dbeta && rows > 0, UC2_ERR_ARG, "layernorm_bwd: bad args");
+    UC2_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma), UC2_ERR_ARG,
+                "layernorm_bwd: pointers must be 16-byte aligned");
+    long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+    const long long cap = 4LL * num_sms();
+    if (blocks > cap) blocks = cap;
+    if (x_is_f32)
+        layernorm_bwd_kernel<true><<<(unsigned)blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows);
+    else
+        layernorm_bwd_kernel<false><<<(unsigned)blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows);
+    return check_last("layernorm_bwd_kernel");
+}
+
+extern "C" UC2_API int uc2_colsum_bf16(const void* x, long long ld, long long rows, int cols, float* out,
+                                       void* stream) {
+    if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(x && out && rows > 0 && cols > 0 && ld >= cols, UC2_ERR_ARG, "colsum_bf16: bad args");
+    UC2_REQUIRE((ld % 8 == 0) && aligned16(x), UC2_ERR_ARG, "colsum_bf16: x must be 16-byte aligned with ld %% 8 == 0");
+    const int col_blocks = (cols + 255) / 256;
+    int row_blocks = (int)((4LL * num_sms() + col_blocks - 1) / col_blocks);
+    long long row_chunk = (rows + row_blocks - 1) / row_blocks;
+    if (row_chunk < 64) row_chunk = 64;
+    row_blocks = (int)((rows + row_chunk - 1) / row_chunk);
+    colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, rows, cols,
+                                                                                      out, (int)row_chunk);
+    return check_last("colsum_bf16_kernel");
+}
