@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Benchmark of the UC2 cross-modal encoder hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload itm|pretrain]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json configs[1]): one uc2_mscoco_itm fine-tuning step of VLXLMRForImageTextRetrieval
+(uc2-base: 12 layers / 768 hidden, XLM-R vocabulary 250 002, random init) on 120 pairs = 40 x (1 positive +
+2 negatives) of 60 tokens + 100 regions (S = 160, no padding): forward, triplet loss, backward, mean over
+ranks, clip_grad_norm_(2.0), AdamW (lr 1e-4 warm-up, betas (0.9, 0.98)), zero_grad -- config/uc2_mscoco_itm.json.
+`--workload pretrain` runs BASELINE.json configs[2] instead (64 x (60 + 100), tasks itm+OT / mlm / mrfr / mrc-kl
+cycled).  Per-GPU work is fixed as N grows (weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from uc2_b200 import batch as UB  # noqa: E402
+from uc2_b200 import synth  # noqa: E402
+from uc2_b200.config import UC2Config, pretraining_shapes, retrieval_shapes  # noqa: E402
+
+PAIRS, TXT, NBB, SAMPLE = 120, 60, 100, 3
+PRE_B = 64
+LR, BETAS, GRAD_NORM, WARMUP_STEPS, TRAIN_STEPS = 1e-4, (0.9, 0.98), 2.0, 5000, 50000
+TASKS = ("itm", "mlm", "mrfr", "mrc-kl")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def flops_per_sample_fwd(S, layers=12):
+    """linear 14.156 MFLOP/token/layer + attention 3072*S FLOP/token/layer."""
+    return S * layers * (14155776 + 3072 * S)
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic workloads
+# --------------------------------------------------------------------------------------------------
+def itm_batch(seed, n=PAIRS):
+    items = synth.make_pairs(n, seed=seed, txt_len=TXT, num_bb=NBB)
+    return UB.collate_itm_rank(items, SAMPLE)
+
+
+def pretrain_batches(seed, n=PRE_B):
+    items = synth.make_pairs(n, seed=seed, txt_len=TXT, num_bb=NBB)
+    nbbs = [NBB] * n
+    targets = [int(x) for x in synth.det_randint(n, 0, 2, seed, 41)]
+    masks = synth.make_img_masks(nbbs, seed)
+    lab = synth.make_mlm_labels([it["input_ids"] for it in items], seed)
+    soft = [synth.make_soft_labels(NBB, seed * 31 + i) for i in range(n)]
+    out = {"itm": UB.collate_itm(items, targets, with_ot=True), "mlm": UB.collate_mlm(items, lab),
+           "mrfr": UB.collate_mrfr(items, masks), "mrc-kl": UB.collate_mrc(items, masks, soft)}
+    out["mlm"]["n_masked"] = int((out["mlm"]["txt_labels"] != -1).sum())
+    return out
+
+
+def pin(batch):
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v):
+            out[k] = v.contiguous().pin_memory()
+        elif isinstance(v, dict):
+            out[k] = pin(v)
+        else:
+            out[k] = v
+    return out
+
+
+def nbytes(batch):
+    n = 0
+    for v in batch.values():
+        if torch.is_tensor(v):
+            n += v.numel() * v.element_size()
+        elif isinstance(v, dict):
+            n += nbytes(v)
+    return n
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------------
+class Clocks(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in o.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference step on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, workload, n_pairs=6):
+    from oracle import uc2_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = UC2Config()
+    fam = O.Family("vlxlmr")
+    shapes = retrieval_shapes(cfg) if workload == "itm" else pretraining_shapes(cfg)
+    sd = {k: v.requires_grad_(True) for k, v in synth.fill_state_dict(shapes, seed=42, perturb=False).items()}
+    m = {k: torch.zeros_like(v) for k, v in sd.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in sd.items()}
+    if workload == "itm":
+        batches = [("rank", itm_batch(7, n_pairs))]
+    else:
+        pb = pretrain_batches(7, n_pairs)
+        batches = [(t, pb[t]) for t in TASKS]
+    times = []
+    for step in range(1, warmup + steps + 1):
+        t0 = time.perf_counter()
+        task, b = batches[(step - 1) % len(batches)]
+        for p in sd.values():
+            p.grad = None
+        if task == "rank":
+            loss = O.forward_retrieval(sd, fam, b).mean()
+        else:
+            loss = O.pretraining_loss(O.forward_pretraining(sd, fam, b, task), task)
+        loss.backward()
+        with torch.no_grad():
+            names = [k for k, p in sd.items() if p.grad is not None]
+            O.clip_grad_norm([sd[k].grad for k in names], GRAD_NORM)
+            lr = LR * O.warmup_linear(step, WARMUP_STEPS, TRAIN_STEPS)
+            for k in names:
+                O.adamw_step(sd[k], sd[k].grad, m[k], v2[k], step, lr, BETAS[0], BETAS[1], 1e-6, 0.0)
+        if step > warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    return n_pairs / (ms / 1e3), ms, n_pairs
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="itm", choices=["itm", "pretrain"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=12, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    per_gpu = PAIRS if args.workload == "itm" else PRE_B
+    wl_name = ("uc2_mscoco_itm finetune step: 120 pairs/GPU = 40 x (1 pos + 2 neg) x (60 tokens + 100 regions), S=160, "
+               "triplet loss + backward + clip + AdamW" if args.workload == "itm" else
+               "uc2_pretrain mixed-task step: 64 x (60 tokens + 100 regions)/GPU, tasks itm+WRA(OT)/mlm/mrfr/mrc-kl cycled")
+    base = {"metric": "pretrain/finetune samples/sec (ITM fine-tune step)" if args.workload == "itm"
+            else "pretrain samples/sec (mixed-task step)",
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": wl_name, "model": "uc2-base 12L/768H vocab 250002 random init",
+                       "per_gpu_batch": per_gpu, "seq_len": TXT + NBB, "dropout": 0.0,
+                       "l2": "working set (1.1 GB fp32 params + >5 GB activations per step) far exceeds the 126 MB L2"}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        warm = min(args.warmup, 1)
+        steps = min(args.steps, 3)
+        val, ms, n = cpu_reference_steps(steps, warm, args.workload)
+        line = dict(base, impl="reference", value=val, ms_per_step=ms, dtype="f32", steps=steps, warmup=warm,
+                    cpu_baseline={"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                  "sample": f"{n} pairs per step (oracle port of the reference step, fp32, all host threads)"},
+                    e2e={"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line))
+        return
+
+    from uc2_b200 import _lib, distributed as D, itm as uitm, model as umodel
+    from uc2_b200.optim import AdamW, warmup_linear
+    from uc2_b200.train import TrainStep
+    from uc2_b200.utils import set_dropout
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (uc2_b200 has no CPU path)")
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    D.init("nccl")
+    dev = torch.device("cuda", D.local_rank())
+    torch.cuda.set_device(dev)
+
+    cfg = UC2Config(num_hidden_layers=args.layers)
+    if args.workload == "itm":
+        model = uitm.VLXLMRForImageTextRetrieval(cfg, 2048, margin=0.2)
+        sd = synth.fill_state_dict(retrieval_shapes(cfg), seed=42, perturb=False)
+    else:
+        model = umodel.VLXLMRForPretraining(cfg, 2048, 1601)
+        sd = synth.fill_state_dict(pretraining_shapes(cfg), seed=42, perturb=False)
+    model.load_state_dict(sd, strict=False)
+    del sd
+    model.to(dev).train()
+    set_dropout(model, 0.0)
+    arena = model._arena()
+    D.broadcast_arena(arena)
+    groups = [{"params": [p for n, p in model.named_parameters()], "weight_decay": 0.0}]
+    opt = AdamW(groups, lr=LR, betas=BETAS)
+    step_fn = TrainStep(model, opt, grad_norm=GRAD_NORM,
+                        lr_fn=lambda s: max(LR * warmup_linear(s, WARMUP_STEPS, TRAIN_STEPS), 1e-8))
+
+    if args.workload == "itm":
+        host = [(None, pin(itm_batch(1000 + rank)))]
+    else:
+        pb = pretrain_batches(1000 + rank)
+        host = [(t, pin(pb[t])) for t in TASKS]
+    resident = [(t, UB.to_device(b, dev)) for t, b in host]
+    torch.cuda.synchronize()
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms) / steps
+
+    def step_resident(i):
+        t, b = resident[i % len(resident)]
+        step_fn(b, t)
+
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_e2e(i):
+        t, hb = host[i % len(host)]
+        b = UB.to_device(hb, dev, non_blocking=True)            # H2D of this step's inputs from pinned memory
+        loss = step_fn(b, t)
+        loss_host.copy_(loss.reshape(1).float(), non_blocking=False)   # D2H read of the step's loss
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    clocks = Clocks(D.local_rank())
+    clocks.start()
+    l0 = _lib.launch_count()
+    ms_step = timed(step_resident, args.steps)
+    launches = (_lib.launch_count() - l0) // args.steps
+    clk = clocks.summary()
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # roofline of the dominant kernel (the tcgen05 GEMM): one extra step with per-launch CUDA events
+    L = _lib.lib()
+    L.uc2_profile_enable(1)
+    step_resident(0)
+    ms_k, work_k, n_k = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_int * 3)()
+    L.uc2_profile_collect(ms_k, work_k, n_k, 3)
+    L.uc2_profile_enable(0)
+    pk = peaks()
+    gemm_tf = work_k[0] / (ms_k[0] * 1e-3) / 1e12 if ms_k[0] > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05/TMEM, all encoder + head GEMMs of one step)",
+            "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"],
+            "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+            "launches_per_step": int(n_k[0]), "gemm_ms_per_step": ms_k[0], "gemm_share_of_step": ms_k[0] / ms_step,
+            "attention_ms_per_step": ms_k[1],
+            "attention_tflops": work_k[1] / (ms_k[1] * 1e-3) / 1e12 if ms_k[1] > 0 else 0.0, "traffic": None}
+
+    if rank != 0:
+        return
+    S = TXT + NBB
+    step_flops = 3 * flops_per_sample_fwd(S, args.layers) * per_gpu
+    line = dict(base, value=per_gpu * world / (ms_step / 1e3), ms_per_step=ms_step, dtype="bf16",
+                e2e={"value": per_gpu * world / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                     "h2d_bytes_per_step": int(np.mean([nbytes(b) for _, b in host])), "d2h_bytes_per_step": 4},
+                gpu_launches=int(launches), clocks=clk, roofline=roof,
+                model_tflops_per_gpu=step_flops / (ms_step * 1e-3) / 1e12,
+                frac_of_bf16_peak={"vs_sustained": step_flops / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"],
+                                   "vs_burst": step_flops / (ms_step * 1e-3) / 1e12 / pk["tf_burst"]})
+    if world == 1 and not args.no_cpu_baseline:
+        val, ms, n = cpu_reference_steps(2, 1, args.workload)
+        line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                "ms_per_step": ms,
+                                "sample": f"{n} pairs per step, 2 timed steps (oracle port of the reference step, fp32)"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

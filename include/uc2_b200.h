@@ -36,6 +36,12 @@ UC2_API int uc2_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 UC2_API long long uc2_launch_count(void);
 
+/* Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline
+ * numbers; off by default).  collect() synchronises, sums duration [ms], algorithmic work [FLOP] and launch
+ * count per kernel kind (0 = GEMM, 1 = attention, 2 = other) into arrays of `kinds` entries and clears. */
+UC2_API int uc2_profile_enable(int on);
+UC2_API int uc2_profile_collect(double* ms_by_kind, double* work_by_kind, int* launches_by_kind, int kinds);
+
 /* ---------------------------------------------------------------------------------------------
  * Dense layers: tcgen05/TMEM GEMM fed by TMA.
  * Replaces every nn.Linear on the path: model/layer.py:76-78 (Q,K,V), 112 (attention out),

@@ -1,0 +1,167 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/uc2_b200.h declares, the
+product path refuses to run without a GPU, host-side module/state_dict contracts, and the world_size-2
+data-parallel logic on gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib_path():
+    from uc2_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib_path())
+    header = open(os.path.join(ROOT, "include", "uc2_b200.h")).read()
+    declared = set(re.findall(r"UC2_API\s+[\w\s\*]+?\b(uc2_\w+)\s*\(", header))
+    assert len(declared) >= 30, declared
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/uc2_b200.h but not exported"
+    from uc2_b200 import _lib
+    assert set(_lib.EXPORTS) <= declared, set(_lib.EXPORTS) - declared
+    lib.uc2_version.restype = ctypes.c_int
+    assert lib.uc2_version() >= 100
+
+
+def test_no_gpu_means_loud_failure():
+    """No CPU fallback: a compute entry point on a box without a usable sm_100 device returns an error code,
+    and the Python modules raise."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = ctypes.CDLL(_lib_path())
+    lib.uc2_last_error.restype = ctypes.c_char_p
+    rc = lib.uc2_cast_f32_bf16(None, None, ctypes.c_longlong(0), None)
+    assert rc < 0 and lib.uc2_last_error()
+    from uc2_b200 import itm
+    m = itm.VLXLMRForImageTextRetrieval(cases.config(1), 2048)
+    with pytest.raises(RuntimeError):
+        m(cases.batch_rank(), compute_loss=False)
+
+
+def test_state_dict_contract_matches_reference_names():
+    """Parameter / state_dict names are the reference's: the shapes table the golden generator
+    loaded into the REFERENCE modules is exactly what our modules expose."""
+    from uc2_b200 import itm, model
+    from uc2_b200.config import pretraining_shapes, retrieval_shapes
+    cfg = cases.config(2)
+    for fam, Pre, Ret, enc in (("vlxlmr", model.VLXLMRForPretraining, itm.VLXLMRForImageTextRetrieval, "roberta"),
+                               ("uniter", model.UniterForPretraining, itm.UniterForImageTextRetrieval, "bert")):
+        c = cases.config(2, family=fam)
+        m = Pre(c, 2048, 1601)
+        names = {n: tuple(p.shape) for n, p in m.named_parameters()}
+        assert names == {k: tuple(v) for k, v in pretraining_shapes(c, fam).items()}
+        sd = m.state_dict()
+        tied = ["feat_regress.weight"] + (["cls.decoder.weight", "cls.decoder.bias"] if fam == "vlxlmr"
+                                          else ["cls.predictions.decoder.weight"])
+        for t in tied:
+            assert t in sd
+        assert sd["feat_regress.weight"].data_ptr() == sd[f"{enc}.img_embeddings.img_linear.weight"].data_ptr()
+        r = Ret(c, 2048)
+        assert {n: tuple(p.shape) for n, p in r.named_parameters()} == \
+            {k: tuple(v) for k, v in retrieval_shapes(c, fam).items()}
+    # no-decay grouping is name based (optim/misc.py:11): img_layer_norm.weight IS decayed
+    from uc2_b200.optim import build_optimizer
+
+    class Opts:
+        weight_decay, optim, learning_rate, betas = 0.01, "adamw", 1e-4, (0.9, 0.98)
+    m = itm.VLXLMRForImageTextRetrieval(cfg, 2048)
+    opt = build_optimizer(m, Opts)
+    decayed = {id(p) for p in opt.param_groups[0]["params"]}
+    byname = dict(m.named_parameters())
+    assert id(byname["roberta.img_embeddings.img_layer_norm.weight"]) in decayed
+    assert id(byname["roberta.embeddings.LayerNorm.weight"]) not in decayed
+    assert id(byname["roberta.encoder.layer.0.output.dense.bias"]) not in decayed
+
+
+def test_init_output_and_from_pretrained(tmp_path):
+    from uc2_b200 import itm
+    import json
+    cfg = cases.config(1)
+    p = tmp_path / "cfg.json"
+    p.write_text(json.dumps(cfg.to_dict()))
+    sd = cases.weights(cfg, "retrieval")
+    sd["roberta.embeddings.LayerNorm.gamma"] = sd.pop("roberta.embeddings.LayerNorm.weight")   # TF-style names
+    sd["roberta.embeddings.LayerNorm.beta"] = sd.pop("roberta.embeddings.LayerNorm.bias")
+    m = itm.VLXLMRForImageTextRetrieval.from_pretrained(str(p), sd, img_dim=2048, margin=0.2)
+    assert torch.equal(m.roberta.embeddings.LayerNorm.weight, sd["roberta.embeddings.LayerNorm.gamma"])
+    m.init_output()
+    assert torch.equal(m.rank_output.weight, m.itm_output.weight[1:])
+    assert torch.equal(m.rank_output.bias, m.itm_output.bias[1:])
+
+
+def test_arena_layout_glues_qkv():
+    from uc2_b200.arena import _order
+    from uc2_b200 import itm
+    m = itm.VLXLMRForImageTextRetrieval(cases.config(2), 2048)
+    names = _order([n for n, _ in m.named_parameters()])
+    i = names.index("roberta.encoder.layer.1.attention.self.query.weight")
+    assert [n.split("self.")[1] for n in names[i:i + 6]] == ["query.weight", "key.weight", "value.weight",
+                                                            "query.bias", "key.bias", "value.bias"]
+    assert sorted(names) == sorted(n for n, _ in m.named_parameters())
+
+
+def test_lr_schedule_and_loss_reduction():
+    from uc2_b200.optim import warmup_linear
+    from uc2_b200.train import reduce_loss
+    assert warmup_linear(5, 10, 100) == 0.5 and warmup_linear(55, 10, 100) == 0.5
+    itm = torch.tensor([1.0, 3.0])
+    pos, neg = torch.tensor([2.0]), torch.tensor([1.0, 1.0])
+    got = reduce_loss((itm, (pos, neg)), "itm", 0.1)
+    assert abs(float(got) - (2.0 + 0.1 * (2.0 - 2.0) / 3)) < 1e-6
+    assert float(reduce_loss(torch.tensor([1.0, 2.0]), "mlm")) == 1.5
+
+
+DP_SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from uc2_b200 import distributed as D
+D.init("gloo")
+r, w = D.rank(), D.size()
+assert w == 2
+flat = torch.arange(1000, dtype=torch.float32) * (r + 1)
+sync = D.GradSync(flat, bucket_bytes=256 * 4)
+sync.ready(600, 1000)        # "heads"
+sync.ready(200, 600)         # "layers"
+sync.finish()                # embeddings [0,200) were never reported: finish() must still reduce them
+exp = torch.arange(1000, dtype=torch.float32) * 1.5
+assert torch.allclose(flat, exp), (flat[:5], exp[:5])
+# disabled (gradient accumulation micro-step): nothing may be communicated
+flat2 = torch.ones(10) * (r + 1)
+s2 = D.GradSync(flat2); s2.enabled = False; s2.ready(0, 10); s2.finish()
+assert torch.equal(flat2, torch.ones(10) * (r + 1))
+t = [torch.ones(3) * (r + 1), torch.ones(2) * (r + 1)]
+D.all_reduce_and_rescale_tensors(t, 2.0)
+assert torch.allclose(t[0], torch.ones(3) * 0.75)
+assert D.all_gather_list({"rank": r}) == [{"rank": 0}, {"rank": 1}]
+assert D.any_broadcast("task_%%d" %% r, 1) == "task_1"
+rows = torch.full((r + 1, 4), float(r))
+allr = D.allgather_rows(rows)
+assert allr.shape == (3, 4) and allr[0, 0] == 0 and allr[2, 0] == 1
+b = torch.zeros(5) + r
+D.broadcast_tensors([b], 0)
+assert torch.equal(b, torch.zeros(5))
+dist.destroy_process_group()
+print("ok", r)
+"""
+
+
+def test_data_parallel_logic_gloo_world2(tmp_path):
+    script = tmp_path / "dp.py"
+    script.write_text(DP_SCRIPT % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 2

@@ -94,6 +94,8 @@ _SIGS = {
     "uc2_f32_to_bf16_2d": [P, LL, P, LL, LL, I, P],
     "uc2_ot_ipot_fwd": [P, P, P, P, I, I, I, I, I, F, I, I, P, P, P, P],
     "uc2_ot_ipot_bwd": [P, P, P, P, I, I, I, I, I, P, P, P, P, P],
+    "uc2_profile_enable": [I],
+    "uc2_profile_collect": [P, P, P, I],
     "uc2_cast_f32_bf16": [P, P, LL, P],
     "uc2_grad_sqnorm": [P, P, I, P, P, P],
     "uc2_adamw_step": [P, P, P, P, P, P, I, P, P, C.POINTER(AdamwHyper), P, P],

@@ -14,6 +14,7 @@ import torch
 from . import _lib
 
 ALIGN = 128   # elements: 512 B in fp32, 256 B in bf16 (TMA needs 16 B, vector kernels 16 B)
+ARENAS = []   # most recent arenas; the optimiser finds the one that owns its parameters
 
 
 def _order(names):
@@ -68,6 +69,8 @@ class ParamArena(object):
         self.active = {n: False for n in names}             # has this tensor ever received a gradient
         self._versions = None
         self.sync_shadow(force=True)
+        ARENAS.append(self)
+        del ARENAS[:-8]
 
     # ------------------------------------------------------------------ views
     def m(self, name):

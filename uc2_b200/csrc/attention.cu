@@ -371,6 +371,7 @@ extern "C" UC2_API int uc2_attention_fwd(const void* qkv, const long long* attn_
     if (int rc = attn_check(B, S, &S_pad)) return rc;
     const int smem = TILE * 128 + 2 * S_pad * 128 + S_pad * 4;
     if (int rc = set_smem(attention_fwd_kernel, smem)) return rc;
+    ProfScope prof((cudaStream_t)stream, 1, 4.0 * B * NH * (double)S * S * HD);
     attention_fwd_kernel<<<dim3(S_pad / TILE, NH, B), ATT_THREADS, smem, (cudaStream_t)stream>>>(
         (const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, S_pad);
     return check_last("attention_fwd_kernel");
@@ -387,6 +388,7 @@ extern "C" UC2_API int uc2_attention_bwd(const void* qkv, const long long* attn_
     if (int rc = attn_check(B, S, &S_pad)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const long long rows = (long long)B * S;
+    ProfScope prof(s, 1, 10.0 * B * NH * (double)S * S * HD);      // 5 S x S x 64 products (7 computed)
     attention_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>((const bf16*)ctx, (const bf16*)dctx, delta_ws, B, S);
     if (int rc = check_last("attention_delta_kernel")) return rc;
     const int smem_dq = 2 * TILE * 128 + 2 * S_pad * 128 + S_pad * 4;

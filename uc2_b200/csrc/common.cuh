@@ -34,6 +34,14 @@ int check_last(const char* what);   // cudaGetLastError -> UC2_ERR_CUDA
     } while (0)
 
 int num_sms();
+
+// RAII launch timer (no-op unless uc2_profile_enable(1)); kind 0 = GEMM, 1 = attention, 2 = other
+struct ProfScope {
+    ProfScope(cudaStream_t s, int kind, double work);
+    ~ProfScope();
+    cudaStream_t stream_;
+    int idx_;
+};
 int require_sm100();
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

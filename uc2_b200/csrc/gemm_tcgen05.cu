@@ -362,7 +362,10 @@ int launch(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
     if (rc) return rc;
     const int total = p.num_m_blocks * p.num_n_blocks * p.split_k;
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+    {
+        ProfScope prof(stream, 0, 2.0 * a.M * a.N * a.K);
+        kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+    }
     return check_last("gemm_bf16_kernel");
 }
 

@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -63,7 +65,57 @@ int require_sm100() {
     return UC2_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// optional per-launch timing with CUDA events on the launching stream (bench.py roofline numbers)
+// ---------------------------------------------------------------------------------------------
+static bool g_prof_on = false;
+struct ProfRec { cudaEvent_t e0, e1; int kind; double work; };
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+
+ProfScope::ProfScope(cudaStream_t s, int kind, double work) : stream_(s), idx_(-1) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    r.kind = kind;
+    r.work = work;
+    cudaEventRecord(r.e0, s);
+    g_prof.push_back(r);
+    idx_ = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx_ < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[idx_].e1, stream_);
+}
+
 }  // namespace uc2
+
+extern "C" UC2_API int uc2_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(uc2::g_prof_mu);
+    uc2::g_prof_on = on != 0;
+    return UC2_OK;
+}
+
+// Sums the recorded launches per kind (0 = GEMM, 1 = attention, 2 = other) and clears the records.
+extern "C" UC2_API int uc2_profile_collect(double* ms_by_kind, double* work_by_kind, int* launches_by_kind, int kinds) {
+    using namespace uc2;
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("profile_collect: sync failed"); return UC2_ERR_CUDA; }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int k = 0; k < kinds; ++k) { ms_by_kind[k] = 0; work_by_kind[k] = 0; launches_by_kind[k] = 0; }
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (r.kind >= 0 && r.kind < kinds) {
+            ms_by_kind[r.kind] += ms; work_by_kind[r.kind] += r.work; launches_by_kind[r.kind] += 1;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    return UC2_OK;
+}
 
 extern "C" UC2_API const char* uc2_last_error(void) { return uc2::g_err; }
 extern "C" UC2_API int uc2_version(void) { return 100; }

@@ -1,0 +1,160 @@
+"""Data-parallel glue: the reference's Horovod helpers (utils/distributed.py) re-expressed over
+torch.distributed (NCCL over NVLink 5 / NVSwitch on the GPU box, gloo in CPU tests).
+
+The reference copies every gradient into one flat fp16 buffer AFTER backward, runs one blocking
+``hvd.allreduce_`` on ~560 MB and copies back (utils/distributed.py:15-42, called at pretrain.py:564-566).
+Here the gradients already live in one contiguous fp32 arena, so a bucket is just a slice: ``GradSync``
+launches one asynchronous all-reduce per bucket as soon as the backward pass has finished writing that slice
+(heads first, then encoder layers from the top, embeddings last) on NCCL's own stream, overlapping the
+remaining backward kernels.  Semantics: mean over ranks (Horovod's default ``average=True`` with
+``rescale_denom=1``; SURVEY 8c notes this is unpinned in the reference).
+"""
+import os
+import pickle
+
+import torch
+import torch.distributed as dist
+
+
+def is_initialized():
+    return dist.is_available() and dist.is_initialized()
+
+
+def size():
+    return dist.get_world_size() if is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if is_initialized() else 0
+
+
+def local_rank():
+    return int(os.environ.get("LOCAL_RANK", 0))
+
+
+def init(backend=None):
+    """One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*)."""
+    if is_initialized() or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return
+    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    if backend == "nccl":
+        torch.cuda.set_device(local_rank())
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank()))
+    else:
+        dist.init_process_group(backend)
+
+
+def _avg_inplace(t, async_op=False):
+    if t.is_cuda:
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+    w = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)      # gloo has no AVG
+    if async_op:
+        return _DivAfter(w, t, size())
+    t.div_(size())
+    return None
+
+
+class _DivAfter(object):
+    def __init__(self, work, t, n):
+        self.work, self.t, self.n = work, t, n
+
+    def wait(self):
+        self.work.wait()
+        self.t.div_(self.n)
+
+
+class GradSync(object):
+    """Bucketed, backward-overlapped gradient averaging over a flat gradient arena."""
+
+    def __init__(self, flat_grad, bucket_bytes=64 << 20):
+        self.flat = flat_grad
+        self.bucket = max(1, bucket_bytes // flat_grad.element_size())
+        self.works = []
+        self.enabled = True
+        self.done = []          # [lo, hi) ranges already submitted in this step
+
+    def ready(self, lo, hi):
+        """The backward pass has finished writing flat[lo:hi]."""
+        if not self.enabled or size() == 1 or hi <= lo:
+            return
+        self.done.append((lo, hi))
+        for s in range(lo, hi, self.bucket):
+            self.works.append(_avg_inplace(self.flat[s:min(s + self.bucket, hi)], async_op=True))
+
+    def finish(self):
+        """Submit whatever was not reported through ready(), then make the compute stream wait."""
+        if self.enabled and size() > 1:
+            covered = sorted(self.done)
+            pos = 0
+            for lo, hi in covered + [(self.flat.numel(), self.flat.numel())]:
+                if lo > pos:
+                    for s in range(pos, lo, self.bucket):
+                        self.works.append(_avg_inplace(self.flat[s:min(s + self.bucket, lo)], async_op=True))
+                pos = max(pos, hi)
+        for w in self.works:
+            if w is not None:
+                w.wait()
+        self.works, self.done = [], []
+
+
+# --------------------------------------------------------------------------------------------------
+# reference-named helpers (utils/distributed.py)
+# --------------------------------------------------------------------------------------------------
+def all_reduce_and_rescale_tensors(tensors, rescale_denom):
+    """utils/distributed.py:15-42: average every tensor over ranks, then divide by rescale_denom."""
+    if size() > 1:
+        works = [_avg_inplace(t, async_op=True) for t in tensors]
+        for w in works:
+            if w is not None:
+                w.wait()
+    if rescale_denom != 1:
+        for t in tensors:
+            t.div_(rescale_denom)
+
+
+def broadcast_tensors(tensors, root_rank, buffer_size=10485760):
+    """utils/distributed.py:99-147 (parameter broadcast from rank 0 at start-up)."""
+    if size() == 1:
+        return
+    for t in tensors:
+        dist.broadcast(t, root_rank)
+
+
+def broadcast_arena(arena, root_rank=0):
+    """One broadcast of the flat master arena (C2 in SURVEY 2.1), then refresh the bf16 shadows."""
+    if size() > 1:
+        dist.broadcast(arena.master, root_rank)
+        arena.sync_shadow(force=True)
+
+
+def all_gather_list(data):
+    """utils/distributed.py:175-204."""
+    if size() == 1:
+        return [data]
+    out = [None] * size()
+    dist.all_gather_object(out, data)
+    return out
+
+
+def any_broadcast(data, root_rank):
+    """utils/distributed.py:207-230."""
+    if size() == 1:
+        return data
+    box = [data]
+    dist.broadcast_object_list(box, src=root_rank)
+    return box[0]
+
+
+def allgather_rows(t):
+    """itm.py:498 ``hvd.allgather(score_matrix)``: concatenate row shards (possibly ragged) over ranks."""
+    if size() == 1:
+        return t
+    n = torch.tensor([t.size(0)], device=t.device)
+    ns = [torch.zeros_like(n) for _ in range(size())]
+    dist.all_gather(ns, n)
+    mx = int(max(int(x) for x in ns))
+    pad = t.new_zeros((mx,) + tuple(t.shape[1:]))
+    pad[:t.size(0)] = t
+    outs = [torch.empty_like(pad) for _ in range(size())]
+    dist.all_gather(outs, pad)
+    return torch.cat([o[:int(k)] for o, k in zip(outs, ns)], 0)

@@ -10,6 +10,7 @@ from . import _lib
 from ._lib import call, ptr, stream
 
 BF16, F32 = torch.bfloat16, torch.float32
+ctypes_size = C.sizeof
 
 
 def _empty(shape, dtype, like):
@@ -134,8 +135,33 @@ def encoder_backward(enc, arena, st, dout):
     ws_bytes = int(_lib.lib().uc2_encoder_bwd_workspace_bytes(B, S))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dout.device)
     dx0 = torch.empty((M, 768), dtype=BF16, device=dout.device)
-    call("uc2_encoder_bwd", st.x0.data_ptr(), st.am.data_ptr(), B, S, L, st.W, st.acts, G, dout.data_ptr(),
-         dx0.data_ptr(), ws.data_ptr(), ws_bytes, stream())
+    sync = getattr(arena, "grad_sync", None)
+    if sync is None or not sync.enabled:
+        call("uc2_encoder_bwd", st.x0.data_ptr(), st.am.data_ptr(), B, S, L, st.W, st.acts, G, dout.data_ptr(),
+             dx0.data_ptr(), ws.data_ptr(), ws_bytes, stream())
+    else:
+        # Data parallel: run the stack in segments of layers (top first) and hand each finished slice of the
+        # gradient arena to the NCCL stream while the next segment computes.
+        q0 = lambda l: arena.offset[pre + f"encoder.layer.{l}.attention.self.query.weight"]
+        last = pre + f"encoder.layer.{L - 1}.output.LayerNorm.bias"
+        layers_end = arena.offset[last] + arena.numel[last]
+        sync.ready(layers_end, arena.total)                 # pooler + heads: complete before this backward runs
+        seg = max(1, getattr(sync, "layers_per_segment", 3))
+        WS, AS, GS = ctypes_size(_lib.LayerWeights), ctypes_size(_lib.LayerActs), ctypes_size(_lib.LayerGrads)
+        d_hi = dout
+        hi = L
+        while hi > 0:
+            lo = max(0, hi - seg)
+            x_in = st.x0 if lo == 0 else st.bufs[lo - 1]["out"]
+            d_lo = dx0 if lo == 0 else torch.empty((M, 768), dtype=BF16, device=dout.device)
+            call("uc2_encoder_bwd", x_in.data_ptr(), st.am.data_ptr(), B, S, hi - lo,
+                 C.cast(C.byref(st.W, lo * WS), C.POINTER(_lib.LayerWeights)),
+                 C.cast(C.byref(st.acts, lo * AS), C.POINTER(_lib.LayerActs)),
+                 C.cast(C.byref(G, lo * GS), C.POINTER(_lib.LayerGrads)),
+                 d_hi.data_ptr(), d_lo.data_ptr(), ws.data_ptr(), ws_bytes, stream())
+            end = layers_end if hi == L else q0(hi)
+            sync.ready(q0(lo), end)
+            d_hi, hi = d_lo, lo
     arena.touch(*enc.layer_param_names())
     # embeddings
     g = _lib.EmbedGrads()
@@ -178,6 +204,8 @@ def encoder_backward(enc, arena, st, dout):
                  arena.gp(ip + "mask_embedding.weight") + 4 * D, 768, D, stream())
             names.append(ip + "mask_embedding.weight")
     arena.touch(*names)
+    if sync is not None and sync.enabled:
+        sync.ready(0, arena.offset[pre + "encoder.layer.0.attention.self.query.weight"])     # embeddings: last
 
 
 class EncoderFn(torch.autograd.Function):

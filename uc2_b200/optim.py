@@ -1,0 +1,199 @@
+"""Optimiser side of the path: AdamW (optim/adamw.py), parameter grouping (optim/misc.py) and LR schedules
+(optim/sched.py) with the reference's names and semantics, executed as ONE kernel launch over the flat
+parameter arena (uc2_adamw_step) instead of ~10 elementwise launches per parameter tensor.
+"""
+import ctypes as C
+from math import ceil
+
+import torch
+
+from . import _lib
+from ._lib import call, stream
+from .arena import ParamArena
+
+CHUNK = 8192
+
+
+def _find_arena(p):
+    from .arena import ARENAS
+    for a in reversed(ARENAS):
+        lo = a.master.data_ptr()
+        if lo <= p.data_ptr() < lo + 4 * a.total and a.intact():
+            return a
+    raise RuntimeError("uc2_b200.optim.AdamW: parameters are not backed by a uc2_b200 parameter arena yet -- run one "
+                       "forward pass on the CUDA device (or call model._arena()) before optimizer.step()")
+
+
+class AdamW(object):
+    """Same constructor and param_groups contract as optim/adamw.py:9-38; step() == adamw.py:40-103.
+
+    Gradient clipping (torch.nn.utils.clip_grad_norm_ at pretrain.py:610 / itm.py:305) is requested with
+    ``clip_grad_norm_(optimizer, max_norm)`` below and fused into the same launch; zero_grad() is fused too.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True):
+        if lr < 0.0:
+            raise ValueError("Invalid learning rate: {} - should be >= 0.0".format(lr))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter: {} - should be in [0.0, 1.0[".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter: {} - should be in [0.0, 1.0[".format(betas[1]))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {} - should be >= 0.0".format(eps))
+        params = list(params)
+        if params and not isinstance(params[0], dict):
+            params = [{"params": params}]
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, correct_bias=correct_bias)
+        self.defaults = defaults
+        self.param_groups = []
+        for g in params:
+            g = dict(g)
+            g["params"] = list(g["params"])
+            for k, v in defaults.items():
+                g.setdefault(k, v)
+            self.param_groups.append(g)
+        if len(self.param_groups) > 8:
+            raise ValueError("at most 8 parameter groups are supported")
+        self.global_step = 0
+        self._arena = None
+        self._pending_clip = 0.0
+        self._fused_zero = True
+        self.state = {}
+
+    # ---------------------------------------------------------------------------------------------
+    def _bind(self):
+        p0 = self.param_groups[0]["params"][0]
+        arena = _find_arena(p0)
+        if arena is self._arena:
+            return
+        self._arena = arena
+        dev = arena.master.device
+        by_ptr = {arena.params[n].data_ptr(): n for n in arena.names}
+        group_of = [-1] * len(arena.names)
+        for gi, g in enumerate(self.param_groups):
+            for p in g["params"]:
+                n = by_ptr.get(p.data_ptr())
+                if n is None:
+                    raise RuntimeError("optimizer parameter is not part of the model's arena")
+                group_of[arena.index[n]] = gi
+        chunks = []
+        for n in arena.names:
+            t, off, num = arena.index[n], arena.offset[n], arena.numel[n]
+            for s in range(0, num, CHUNK):
+                chunks.append((off + s, min(CHUNK, num - s), t))
+        arr = (_lib.OptChunk * len(chunks))()
+        for i, (o, c, t) in enumerate(chunks):
+            arr[i].offset, arr[i].n, arr[i].tensor = o, c, t
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self._chunks = raw.to(dev)
+        self._n_chunks = len(chunks)
+        self._group_of = torch.tensor(group_of, dtype=torch.int32, device=dev)
+        self._group_of_host = group_of
+        self._act_host = [-1] * len(arena.names)
+        self._act = torch.full((len(arena.names),), -1, dtype=torch.int32, device=dev)
+        self.exp_avg = torch.zeros_like(arena.master)
+        self.exp_avg_sq = torch.zeros_like(arena.master)
+        self._sqnorm = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def _refresh_active(self, step):
+        a = self._arena
+        changed = False
+        for n in a.names:
+            t = a.index[n]
+            if a.active[n] and self._act_host[t] < 0 and self._group_of_host[t] >= 0:
+                self._act_host[t] = step
+                changed = True
+        if changed:
+            self._act.copy_(torch.tensor(self._act_host, dtype=torch.int32), non_blocking=False)
+
+    def grad_norm(self):
+        """Global L2 norm of the gradients of every tensor that has one (device tensor, no host sync)."""
+        self._bind()
+        self._refresh_active(self.global_step + 1)
+        a = self._arena
+        call("uc2_grad_sqnorm", a.grad.data_ptr(), self._chunks.data_ptr(), self._n_chunks, self._act.data_ptr(),
+             self._sqnorm.data_ptr(), stream())
+        return self._sqnorm.sqrt().float()
+
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self._bind()
+        self.global_step += 1
+        self._refresh_active(self.global_step)
+        a = self._arena
+        h = _lib.AdamwHyper()
+        g0 = self.param_groups[0]
+        for gi, g in enumerate(self.param_groups):
+            h.lr[gi] = g["lr"]
+            h.weight_decay[gi] = g["weight_decay"]
+            if g["betas"] != g0["betas"] or g["eps"] != g0["eps"] or g["correct_bias"] != g0["correct_bias"]:
+                raise NotImplementedError("per-group betas/eps/correct_bias are not used by the reference")
+        h.beta1, h.beta2, h.eps = g0["betas"][0], g0["betas"][1], g0["eps"]
+        h.correct_bias, h.global_step = int(g0["correct_bias"]), self.global_step
+        h.max_grad_norm = float(self._pending_clip)
+        h.zero_grad = int(self._fused_zero)
+        call("uc2_adamw_step", a.master.data_ptr(), a.grad.data_ptr(), self.exp_avg.data_ptr(),
+             self.exp_avg_sq.data_ptr(), a.shadow.data_ptr(), self._chunks.data_ptr(), self._n_chunks,
+             self._act.data_ptr(), self._group_of.data_ptr(), C.byref(h),
+             self._sqnorm.data_ptr() if self._pending_clip > 0 else None, stream())
+        self._pending_clip = 0.0
+        a.mark_synced()
+        return loss
+
+    def zero_grad(self, set_to_none=False):
+        """Gradients were already cleared inside step() (fused); tensors that never had a gradient are zero."""
+        if not self._fused_zero and self._arena is not None:
+            self._arena.zero_grad()
+
+    def state_dict(self):
+        return {"global_step": self.global_step, "act": list(getattr(self, "_act_host", [])),
+                "exp_avg": getattr(self, "exp_avg", None), "exp_avg_sq": getattr(self, "exp_avg_sq", None),
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+
+def clip_grad_norm_(optimizer, max_norm):
+    """pretrain.py:610 ``clip_grad_norm_(amp.master_params(optimizer), opts.grad_norm)``: returns the total
+    norm (device tensor) and arms the clip coefficient for the next optimizer.step()."""
+    total = optimizer.grad_norm()
+    optimizer._pending_clip = float(max_norm)
+    return total
+
+
+# ---- optim/misc.py:9-32 -------------------------------------------------------------------------------
+def build_optimizer(model, opts):
+    param_optimizer = list(model.named_parameters())
+    no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
+    optimizer_grouped_parameters = [
+        {"params": [p for n, p in param_optimizer if not any(nd in n for nd in no_decay)],
+         "weight_decay": opts.weight_decay},
+        {"params": [p for n, p in param_optimizer if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    if opts.optim != "adamw":
+        raise ValueError("invalid optimizer (the B200 path implements adamw, the optimiser both shipped configs use)")
+    return AdamW(optimizer_grouped_parameters, lr=opts.learning_rate, betas=opts.betas)
+
+
+# ---- optim/sched.py -----------------------------------------------------------------------------------
+def noam_schedule(step, warmup_step=4000):
+    if step <= warmup_step:
+        return step / warmup_step
+    return (warmup_step ** 0.5) * (step ** -0.5)
+
+
+def warmup_linear(step, warmup_step, tot_step):
+    if step < warmup_step:
+        return step / warmup_step
+    return max(0, (tot_step - step) / (tot_step - warmup_step))
+
+
+def get_lr_sched(global_step, opts):
+    if opts.decay == "linear":
+        lr_this_step = opts.learning_rate * warmup_linear(global_step, opts.warmup_steps, opts.num_train_steps)
+    elif opts.decay == "invsqrt":
+        lr_this_step = opts.learning_rate * noam_schedule(global_step, opts.warmup_steps)
+    elif opts.decay == "constant":
+        lr_this_step = opts.learning_rate
+    else:
+        raise ValueError("unsupported decay")
+    if lr_this_step <= 0:
+        lr_this_step = 1e-8
+    return lr_this_step

@@ -1,0 +1,81 @@
+"""One optimizer step of the reference training loops around the B200 modules
+(pretrain.py:514-650 and itm.py:253-358 without horovod / apex / tensorboard):
+
+    forward -> loss reduction -> backward -> (mean over ranks, overlapped with backward)
+            -> lr schedule -> clip_grad_norm_ -> AdamW.step -> zero_grad
+
+Differences from the reference that are deliberate: no per-step pickled all-gathers of the task name
+(pretrain.py:517 -- every rank derives the same task from the step number), no .item() host syncs per
+micro-step, bf16 + fp32 masters instead of apex O2 loss scaling.
+"""
+import torch
+
+from . import distributed as D
+from .optim import clip_grad_norm_
+
+
+def reduce_loss(out, task, itm_ot_lambda=0.1, ot_pos_only=False):
+    """pretrain.py:524-553."""
+    if task is None:
+        return out.mean()
+    if task.startswith("itm"):
+        itm_loss, ot_loss = out
+        loss = itm_loss.mean()
+        if ot_loss is not None:
+            if not ot_pos_only:
+                ot_pos, ot_neg = ot_loss
+                ot = (ot_pos.sum() - ot_neg.sum()) / (ot_pos.size(0) + ot_neg.size(0))
+            else:
+                ot = ot_loss.mean()
+            loss = loss + itm_ot_lambda * ot
+        return loss
+    if task.startswith("vmlm-soft"):
+        return 1000 * out.mean()
+    return out.mean()
+
+
+class TrainStep(object):
+    def __init__(self, model, optimizer, grad_norm=-1.0, gradient_accumulation_steps=1, itm_ot_lambda=0.1,
+                 lr_fn=None, bucket_bytes=64 << 20, layers_per_segment=3):
+        self.model, self.optimizer = model, optimizer
+        self.grad_norm = grad_norm
+        self.accum = gradient_accumulation_steps
+        self.lam = itm_ot_lambda
+        self.lr_fn = lr_fn
+        self.micro = 0
+        self.global_step = 0
+        self.bucket_bytes = bucket_bytes
+        self.layers_per_segment = layers_per_segment
+        self.sync = None
+
+    def _ensure_sync(self):
+        arena = self.model._arena()
+        if D.size() > 1 and (self.sync is None or self.sync.flat.data_ptr() != arena.grad.data_ptr()):
+            self.sync = D.GradSync(arena.grad, self.bucket_bytes)
+            self.sync.layers_per_segment = self.layers_per_segment
+            arena.grad_sync = self.sync
+        return arena
+
+    def __call__(self, batch, task=None):
+        """One micro-step; runs the optimizer when the accumulation window closes.  Returns the (device) loss."""
+        self._ensure_sync()
+        last = (self.micro + 1) % self.accum == 0
+        if self.sync is not None:
+            self.sync.enabled = last               # only the last micro-step's backward triggers communication
+        out = self.model(batch, task=task, compute_loss=True) if task is not None else self.model(batch, compute_loss=True)
+        loss = reduce_loss(out, task, self.lam, getattr(self.model, "ot_pos_only", False))
+        loss.backward()
+        self.micro += 1
+        if last:
+            if self.sync is not None:
+                self.sync.finish()
+            self.global_step += 1
+            if self.lr_fn is not None:
+                lr = self.lr_fn(self.global_step)
+                for g in self.optimizer.param_groups:
+                    g["lr"] = lr
+            if self.grad_norm != -1 and self.grad_norm > 0:
+                clip_grad_norm_(self.optimizer, self.grad_norm)
+            self.optimizer.step()
+            self.optimizer.zero_grad()
+        return loss.detach()
