@@ -97,10 +97,29 @@ __device__ __forceinline__ void store8_f32(float* p, const float* f) {
     *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
-// erf-form GELU (model/layer.py:31-37) and its derivative
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-form GELU (model/layer.py:31-37) and its derivative.
+// Phi(x) = 0.5 erfc(-x/sqrt2) through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e. far below
+// one bf16 ulp): erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z), z >= 0.
+// Written on the erfc side so that the negative tail has no 1 + erf cancellation; one MUFU.RCP + one
+// MUFU.EX2 per element, and exp(-z^2) = exp(-x^2/2) is shared with the density term of the derivative.
+struct GeluTerms { float Phi, e; };
+__device__ __forceinline__ GeluTerms gelu_terms(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    GeluTerms g;
+    g.e = exp2f(-1.4426950408889634f * z * z);
+    const float h = 0.5f * pl * t * g.e;          // 0.5 erfc(|x|/sqrt2)
+    g.Phi = x < 0.f ? h : 1.0f - h;
+    return g;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_terms(x).Phi; }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+    const GeluTerms g = gelu_terms(x);
+    return fmaf(x * 0.3989422804014327f, g.e, g.Phi);
 }
 
 #endif  // __CUDACC__

@@ -5,8 +5,11 @@
 // split-K with fp32 atomic accumulation).  Replaces the nn.Linear call sites listed in
 // include/uc2_b200.h (model/layer.py:76-78,112,140,153; model/model.py:359,1153-1169).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue.  An epilogue warp owns TMEM lane quarter warp_idx % 4 (the hardware's rule) and
+// every other 32-column chunk of the accumulator; a thread owns one output row of a chunk, so all the
+// residual / aux / bias loads of a chunk are in flight together (no shared-memory transpose) while the
+// tcgen05.ld of the accumulator is outstanding, and the epilogue of tile i hides under the MMAs of tile i+1.
 #include <mutex>
 
 #include "common.cuh"
@@ -19,10 +22,10 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_COLS = 32;   // accumulator columns moved TMEM -> smem -> global per step
-constexpr int STAGE_LD = 36;   // fp32 words per staged row (32 + 4 pad: conflict-free 128-bit access)
-constexpr int STAGING_BYTES = 4 * 32 * STAGE_LD * 4;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_COLS = 32;   // accumulator columns per tcgen05.ld (one fp32 row slice of 128 B per thread)
+constexpr int STAGING_BYTES = 0;
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
 template <int BLOCK_N>
@@ -47,7 +50,7 @@ struct GemmParams {
     bf16* out_pre; long long ld_pre;
     float* out_f32; long long ld_f32;
     int accumulate;
-    int vec_ok;   // all leading dimensions and N are multiples of 4 -> vector epilogue
+    int vec_ok;   // leading dimensions / pointers allow 16-byte row-slice access -> vector epilogue
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float aux) {
@@ -65,7 +68,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-    float* staging = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES);
     const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES + STAGING_BYTES;
     // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -89,7 +91,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull_bar(a), 1);
-            ptx::mbar_init(tempty_bar(a), 4);   // one arrive per epilogue warp
+            ptx::mbar_init(tempty_bar(a), EPI_WARPS);   // one arrive per epilogue warp
         }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -182,7 +184,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else {
         // ===================================== epilogue =========================================
         const int q = warp_idx & 3;                       // TMEM lane quarter owned by this warp
-        float* stg = staging + (warp_idx - 2) * 32 * STAGE_LD;
+        const int half = (warp_idx - 2) >> 2;             // which of the interleaved 32-column chunks
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -190,105 +192,149 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            const int row0 = m_blk * BLOCK_M + q * 32;
+            const long long grow = (long long)m_blk * BLOCK_M + q * 32 + lane;
+            const bool row_ok = grow < p.M;
+            constexpr int MY_CHUNKS = BLOCK_N / EPI_COLS / 2;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
+            for (int i = 0; i < MY_CHUNKS; ++i) {
+                const int c = 2 * i + half;
+                const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * EPI_COLS,
                                    r);
+                // operands of the fused epilogue, requested while the accumulator load is in flight
+                const bool vec = p.vec_ok && col0 + EPI_COLS <= p.N;       // warp-uniform
+                const bool live = row_ok && col0 < p.N;
+                uint4 ex[8];                                               // residual (fp32: 8 x 16 B, bf16: 4) or aux
+                if (vec && live) {
+                    if (p.residual) {
+                        if (p.res_f32) {
+                            const uint4* src = reinterpret_cast<const uint4*>(
+                                reinterpret_cast<const float*>(p.residual) + grow * p.ld_res + col0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) ex[j] = __ldg(src + j);
+                        } else {
+                            const uint4* src = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) ex[j] = __ldg(src + j);
+                        }
+                    } else if (p.act == UC2_ACT_DGELU) {
+                        const uint4* src = reinterpret_cast<const uint4*>(p.aux + grow * p.ld_aux + col0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ex[j] = __ldg(src + j);
+                    }
+                }
                 ptx::tmem_wait_ld();
-                if (c == BLOCK_N / EPI_COLS - 1) {
+                if (i == MY_CHUNKS - 1) {
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
                 }
-                const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
-                if (col0 >= p.N) continue;                // warp-uniform
-                // thread `lane` holds row (row0+lane): transpose through smem for coalesced global access
+                if (!live) continue;
+                if (vec) {
+                    float v[32];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(stg + lane * STAGE_LD + 4 * j) =
-                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                __syncwarp();
-                const int cq = (lane & 7) * 4;
-                const int gcol = col0 + cq;
-#pragma unroll 2
-                for (int it = 0; it < 8; ++it) {
-                    const int rr = it * 4 + (lane >> 3);
-                    const long long grow = row0 + rr;
-                    if (grow >= p.M || gcol >= p.N) continue;
-                    float4 v4 = *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + cq);
-                    float v[4] = {v4.x, v4.y, v4.z, v4.w};
-                    if (p.vec_ok) {
-                        if (p.bias) {
-                            const float4 b = *reinterpret_cast<const float4*>(p.bias + gcol);
-                            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-                        }
-                        if (p.out_pre) {
-                            uint2 o = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-                            *reinterpret_cast<uint2*>(p.out_pre + grow * p.ld_pre + gcol) = o;
-                        }
-                        if (p.act != UC2_ACT_NONE) {
-                            float a[4] = {0.f, 0.f, 0.f, 0.f};
-                            if (p.act == UC2_ACT_DGELU) {
-                                const uint2 u = *reinterpret_cast<const uint2*>(p.aux + grow * p.ld_aux + gcol);
-                                const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y);
-                                a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y;
-                            }
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = apply_act(v[e], p.act, a[e]);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                         }
-                        if (p.residual) {
-                            if (p.res_f32) {
-                                const float4 r4 = *reinterpret_cast<const float4*>(
-                                    reinterpret_cast<const float*>(p.residual) + grow * p.ld_res + gcol);
-                                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-                            } else {
-                                const uint2 u = *reinterpret_cast<const uint2*>(p.residual + grow * p.ld_res + gcol);
-                                const float2 r0 = unpack_bf16(u.x), r1 = unpack_bf16(u.y);
-                                v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-                            }
-                        }
-                        if (p.out_bf16) {
-                            uint2 o = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-                            *reinterpret_cast<uint2*>(p.out_bf16 + grow * p.ld_out + gcol) = o;
-                        }
-                        if (p.out_f32) {
-                            float* dst = p.out_f32 + grow * p.ld_f32 + gcol;
-                            if (p.accumulate) {
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]),
-                                             "f"(v[1]), "f"(v[2]), "f"(v[3])
-                                             : "memory");
-                            } else {
-                                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                            }
-                        }
-                    } else {
+                    }
+                    if (p.out_pre) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.out_pre + grow * p.ld_pre + col0);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int gc = gcol + e;
-                            if (gc >= p.N) break;
-                            float x = v[e];
-                            if (p.bias) x += p.bias[gc];
-                            if (p.out_pre) p.out_pre[grow * p.ld_pre + gc] = __float2bfloat16(x);
-                            if (p.act != UC2_ACT_NONE) {
-                                const float a =
-                                    p.act == UC2_ACT_DGELU ? __bfloat162float(p.aux[grow * p.ld_aux + gc]) : 0.f;
-                                x = apply_act(x, p.act, a);
-                            }
-                            if (p.residual)
-                                x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[grow * p.ld_res + gc]
-                                               : __bfloat162float(p.residual[grow * p.ld_res + gc]);
-                            if (p.out_bf16) p.out_bf16[grow * p.ld_out + gc] = __float2bfloat16(x);
-                            if (p.out_f32) {
-                                if (p.accumulate) atomicAdd(p.out_f32 + grow * p.ld_f32 + gc, x);
-                                else p.out_f32[grow * p.ld_f32 + gc] = x;
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                    }
+                    if (p.act == UC2_ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    } else if (p.act == UC2_ACT_TANH) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+                    } else if (p.act == UC2_ACT_DGELU && !p.residual) {
+                        const uint32_t* a = reinterpret_cast<const uint32_t*>(ex);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 u = unpack_bf16(a[j]);
+                            v[2 * j] *= gelu_erf_grad(u.x);
+                            v[2 * j + 1] *= gelu_erf_grad(u.y);
+                        }
+                    } else if (p.act == UC2_ACT_DGELU) {
+                        // residual and aux together (not used by the encoder): aux fetched late
+                        const uint32_t* a = reinterpret_cast<const uint32_t*>(p.aux + grow * p.ld_aux + col0);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 u = unpack_bf16(__ldg(a + j));
+                            v[2 * j] *= gelu_erf_grad(u.x);
+                            v[2 * j + 1] *= gelu_erf_grad(u.y);
+                        }
+                    }
+                    if (p.residual) {
+                        if (p.res_f32) {
+                            const float* f = reinterpret_cast<const float*>(ex);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += f[j];
+                        } else {
+                            const uint32_t* a = reinterpret_cast<const uint32_t*>(ex);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 u = unpack_bf16(a[j]);
+                                v[2 * j] += u.x;
+                                v[2 * j + 1] += u.y;
                             }
                         }
                     }
+                    if (p.out_bf16) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld_out + col0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                    }
+                    if (p.out_f32) {
+                        float* dst = p.out_f32 + grow * p.ld_f32 + col0;
+                        if (p.accumulate) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                                             "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                                             : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                reinterpret_cast<float4*>(dst)[j] =
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
+                    }
+                } else {
+                    // ragged right edge or unaligned leading dimensions: scalar path
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int gc = col0 + j;
+                        if (gc >= p.N) continue;
+                        float x = __uint_as_float(r[j]);
+                        if (p.bias) x += p.bias[gc];
+                        if (p.out_pre) p.out_pre[grow * p.ld_pre + gc] = __float2bfloat16(x);
+                        if (p.act != UC2_ACT_NONE) {
+                            const float a =
+                                p.act == UC2_ACT_DGELU ? __bfloat162float(p.aux[grow * p.ld_aux + gc]) : 0.f;
+                            x = apply_act(x, p.act, a);
+                        }
+                        if (p.residual)
+                            x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[grow * p.ld_res + gc]
+                                           : __bfloat162float(p.residual[grow * p.ld_res + gc]);
+                        if (p.out_bf16) p.out_bf16[grow * p.ld_out + gc] = __float2bfloat16(x);
+                        if (p.out_f32) {
+                            if (p.accumulate) atomicAdd(p.out_f32 + grow * p.ld_f32 + gc, x);
+                            else p.out_f32[grow * p.ld_f32 + gc] = x;
+                        }
+                    }
                 }
-                __syncwarp();
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
@@ -450,15 +496,12 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
     p.out_pre = static_cast<bf16*>(a.out_pre); p.ld_pre = a.ld_pre;
     p.out_f32 = a.out_f32; p.ld_f32 = a.ld_f32;
     p.accumulate = a.accumulate;
-    p.vec_ok = (a.N % 4 == 0) && (!a.residual || a.ld_res % 4 == 0) && (!a.aux || a.ld_aux % 4 == 0) &&
-               (!a.out_bf16 || a.ld_out % 4 == 0) && (!a.out_pre || a.ld_pre % 4 == 0) &&
-               (!a.out_f32 || a.ld_f32 % 4 == 0) &&
-               (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) &&
-               (!a.out_f32 || (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0) &&
-               (!a.out_bf16 || (reinterpret_cast<uintptr_t>(a.out_bf16) & 7) == 0) &&
-               (!a.out_pre || (reinterpret_cast<uintptr_t>(a.out_pre) & 7) == 0) &&
-               (!a.residual || (reinterpret_cast<uintptr_t>(a.residual) & (a.residual_f32 ? 15 : 7)) == 0) &&
-               (!a.aux || (reinterpret_cast<uintptr_t>(a.aux) & 7) == 0);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    p.vec_ok = (!a.residual || (a.ld_res % (a.residual_f32 ? 4 : 8) == 0 && al16(a.residual))) &&
+               (!a.aux || (a.ld_aux % 8 == 0 && al16(a.aux))) &&
+               (!a.out_bf16 || (a.ld_out % 8 == 0 && al16(a.out_bf16))) &&
+               (!a.out_pre || (a.ld_pre % 8 == 0 && al16(a.out_pre))) &&
+               (!a.out_f32 || (a.ld_f32 % 4 == 0 && al16(a.out_f32))) && (!a.bias || al16(a.bias));
     int bn = a.block_n;
     if (bn == 0) bn = pick_block_n(a.M, a.N, p.split_k);
     UC2_REQUIRE(bn == 64 || bn == 128 || bn == 256, UC2_ERR_ARG, "uc2_gemm_bf16: block_n must be 64/128/256");
