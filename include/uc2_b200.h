@@ -82,6 +82,7 @@ typedef struct {
     int split_k;      /* >= 1 */
     int block_n;      /* 0 = auto; else 64, 128 or 256 */
     int residual_f32; /* residual points at fp32 (the fp32 residual stream of the encoder) instead of bf16 */
+    int ctas;         /* 0 = auto; 1 = one CTA per 128-row tile; 2 = CTA pair (cta_group::2) per 256-row tile */
 } uc2_gemm_args;
 
 UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream);

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=19200)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--block-n", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0)
     a = ap.parse_args()
     M, H, F, Q = a.tokens, 768, 3072, 2304
     dev = "cuda"
@@ -33,6 +34,8 @@ def main():
     dw = {k: torch.zeros(s, dtype=f32, device=dev) for k, s in
           dict(qkv=(Q, H), o=(H, H), f1=(F, H), f2=(H, F)).items()}
     bn = a.block_n
+    import functools
+    _lib.gemm = functools.partial(_lib.gemm, ctas=a.ctas)
     cases = [
         ("fwd QKV      bias                 ", M, Q, H, lambda: _lib.gemm(x, w_qkv, M, Q, H, bias=bias[Q], out_bf16=o2304, block_n=bn)),
         ("fwd O-proj   bias+res32 -> f32    ", M, H, H, lambda: _lib.gemm(x, w_o, M, H, H, bias=bias[H], residual=res32, out_f32=z32, block_n=bn)),

@@ -128,3 +128,55 @@ def test_bad_args_raise():
     out = torch.zeros(128, 128, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(RuntimeError):
         _lib.gemm(a, b, 128, 128, 70, out_bf16=out)     # pitch not a multiple of 8 elements
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(512, 768, 768), (2400, 2304, 768), (300, 3072, 768), (1333, 768, 3072),
+                                   (129, 1601, 768)])
+def test_cta_pair_forward_and_epilogues(M, N, K, block_n, ctas):
+    """CTA-pair (cta_group::2, 256-row tiles) and single-CTA forms of the same GEMM, every fused epilogue,
+    ragged M (a pair whose second CTA is partly or wholly out of range) and ragged N."""
+    from uc2_b200 import _lib
+    a = _rand((M, K), 21).bfloat16()
+    b = _rand((N, K), 22, 0.05).bfloat16()
+    bias = _rand((N,), 23)
+    Np = (N + 15) // 16 * 16
+    res32 = _rand((M, Np), 24)[:, :N]
+    resb = _rand((M, Np), 25).bfloat16()[:, :N]
+    pre = a.float() @ b.float().t() + bias
+    kw = dict(block_n=block_n, ctas=ctas)
+    z = torch.empty(M, Np, dtype=torch.float32, device="cuda")[:, :N]
+    _lib.gemm(a, b, M, N, K, bias=bias, residual=res32, out_f32=z, **kw)
+    _check(z, pre + res32, 2e-5, "fp32 residual -> fp32")
+    zb = torch.empty(M, Np, dtype=torch.bfloat16, device="cuda")[:, :N]
+    _lib.gemm(a, b, M, N, K, bias=bias, residual=resb, out_bf16=zb, **kw)
+    _check(zb, pre + resb.float(), 1e-2, "bf16 residual")
+    g = torch.empty(M, Np, dtype=torch.bfloat16, device="cuda")[:, :N]
+    u = torch.empty(M, Np, dtype=torch.bfloat16, device="cuda")[:, :N]
+    _lib.gemm(a, b, M, N, K, bias=bias, act=_lib.ACT_GELU, out_bf16=g, out_pre=u, **kw)
+    _check(u, pre, 1e-2, "pre-activation")
+    _check(g, _ref_gelu(pre), 1e-2, "gelu")
+    d = torch.empty(M, Np, dtype=torch.bfloat16, device="cuda")[:, :N]
+    _lib.gemm(a, b, M, N, K, aux=u, act=_lib.ACT_DGELU, out_bf16=d, **kw)
+    _check(d, (a.float() @ b.float().t()) * _ref_dgelu(u.float()), 1e-2, "dgelu")
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_cta_pair_dgrad_wgrad(block_n, ctas):
+    from uc2_b200 import _lib
+    M, N, K = 1000, 768, 3072
+    dy = _rand((M, K), 31).bfloat16()
+    w = _rand((K, N), 32, 0.05).bfloat16()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    _lib.gemm(dy, w, M, N, K, b_mn=True, out_bf16=out, block_n=block_n, ctas=ctas)
+    _check(out, dy.float() @ w.float(), 1e-2, "dgrad")
+    Mtok, N2, K2 = 2500, 3072, 768
+    dy2 = _rand((Mtok, N2), 33).bfloat16()
+    x = _rand((Mtok, K2), 34).bfloat16()
+    for split in (0, 1, 5):
+        dw = torch.ones(N2, K2, dtype=torch.float32, device="cuda")
+        _lib.gemm(dy2, x, N2, K2, Mtok, a_mn=True, b_mn=True, out_f32=dw, accumulate=True, split_k=split,
+                  block_n=block_n, ctas=ctas)
+        _check(dw, dy2.float().t() @ x.float() + 1.0, 1e-4, f"wgrad split {split}")

@@ -102,16 +102,31 @@ __device__ __forceinline__ void store8_f32(float* p, const float* f) {
 // one bf16 ulp): erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z), z >= 0.
 // Written on the erfc side so that the negative tail has no 1 + erf cancellation; one MUFU.RCP + one
 // MUFU.EX2 per element, and exp(-z^2) = exp(-x^2/2) is shared with the density term of the derivative.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// tanh(x) = 1 - 2 / (exp(2x) + 1): two MUFU ops, absolute error ~1e-6 (BertPooler, model/layer.py:184)
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = fast_ex2(fminf(2.8853900817779268f * x, 80.f));
+    return 1.0f - 2.0f * fast_rcp(e + 1.0f);
+}
 struct GeluTerms { float Phi, e; };
 __device__ __forceinline__ GeluTerms gelu_terms(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
     float pl = fmaf(1.061405429f, t, -1.453152027f);
     pl = fmaf(pl, t, 1.421413741f);
     pl = fmaf(pl, t, -0.284496736f);
     pl = fmaf(pl, t, 0.254829592f);
     GeluTerms g;
-    g.e = exp2f(-1.4426950408889634f * z * z);
+    g.e = fast_ex2(-1.4426950408889634f * z * z);
     const float h = 0.5f * pl * t * g.e;          // 0.5 erfc(|x|/sqrt2)
     g.Phi = x < 0.f ? h : 1.0f - h;
     return g;

@@ -5,11 +5,18 @@
 // split-K with fp32 atomic accumulation).  Replaces the nn.Linear call sites listed in
 // include/uc2_b200.h (model/layer.py:76-78,112,140,153; model/model.py:359,1153-1169).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// CTAS = 2 runs the kernel as CTA pairs (thread-block clusters of two on one TPC, tcgen05 cta_group::2):
+// a pair owns a 256 x BLOCK_N tile, each CTA stages its 128 rows of A and its half of the B rows, so a
+// B byte is read from L2 and written to shared memory once per 256 output rows instead of once per 128
+// (the 128-row form is L2- and shared-memory-bandwidth bound well below the tensor-pipe rate).
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (leader CTA),
 // warps 2..9 = epilogue.  An epilogue warp owns TMEM lane quarter warp_idx % 4 (the hardware's rule) and
-// every other 32-column chunk of the accumulator; a thread owns one output row of a chunk, so all the
-// residual / aux / bias loads of a chunk are in flight together (no shared-memory transpose) while the
-// tcgen05.ld of the accumulator is outstanding, and the epilogue of tile i hides under the MMAs of tile i+1.
+// every other 32-column chunk of the accumulator; a thread owns one output row of a chunk and moves it
+// with 256-bit global accesses (one whole 32-byte sector per thread per instruction, nothing goes through
+// shared memory, whose bandwidth belongs to the MMAs).  The residual / dGELU operand of a tile is requested
+// BEFORE the accumulator is complete, so those loads fly while the MMAs of the tile still run, and the
+// epilogue of tile i hides under the MMAs of tile i+1 (two accumulator buffers).
 #include <mutex>
 
 #include "common.cuh"
@@ -19,29 +26,29 @@ namespace uc2 {
 
 namespace {
 
-constexpr int BLOCK_M = 128;
+constexpr int BLOCK_M = 128;   // rows per CTA; a CTA pair covers 2 x BLOCK_M
 constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_COLS = 32;   // accumulator columns per tcgen05.ld (one fp32 row slice of 128 B per thread)
-constexpr int STAGING_BYTES = 0;
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 struct Cfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int B_ROWS = BLOCK_N / CTAS;            // B rows (n) staged by one CTA
+    static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - STAGING_BYTES - 256) / STAGE_BYTES;
+    static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - 256) / STAGE_BYTES;
     static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;   // two accumulator buffers; 128/256/512: power of two
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 256;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
 };
 
 struct GemmParams {
     int M, N, K;
-    int num_m_blocks, num_n_blocks, split_k, k_blocks_per_split, num_k_blocks;
+    int num_m_blocks, num_n_blocks, split_k, k_blocks_per_split, num_k_blocks;   // m blocks of BLOCK_M * CTAS rows
     const float* bias;
     const bf16* residual; long long ld_res; int res_f32;
     const bf16* aux; long long ld_aux;
@@ -50,25 +57,187 @@ struct GemmParams {
     bf16* out_pre; long long ld_pre;
     float* out_f32; long long ld_f32;
     int accumulate;
-    int vec_ok;   // leading dimensions / pointers allow 16-byte row-slice access -> vector epilogue
+    int vec_ok;   // leading dimensions / pointers allow 32-byte row-slice access -> vector epilogue
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float aux) {
     if (act == UC2_ACT_GELU) return gelu_erf(v);
     if (act == UC2_ACT_DGELU) return v * gelu_erf_grad(aux);
-    if (act == UC2_ACT_TANH) return tanhf(v);
+    if (act == UC2_ACT_TANH) return fast_tanh(v);
     return v;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+__device__ __forceinline__ void store_bf16_row16(bf16* dst, const float* v) {
+    ptx::stg256(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]),
+                pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+}
+
+__device__ __noinline__ void epilogue_scalar_row(const GemmParams& p, const float* acc, long long grow, int col0) {
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) {
+        const int gc = col0 + j;
+        if (gc >= p.N) break;
+        float x = acc[j];
+        if (p.bias) x += p.bias[gc];
+        if (p.out_pre) p.out_pre[grow * p.ld_pre + gc] = __float2bfloat16(x);
+        if (p.act != UC2_ACT_NONE) {
+            const float a = p.act == UC2_ACT_DGELU ? __bfloat162float(p.aux[grow * p.ld_aux + gc]) : 0.f;
+            x = apply_act(x, p.act, a);
+        }
+        if (p.residual)
+            x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[grow * p.ld_res + gc]
+                           : __bfloat162float(p.residual[grow * p.ld_res + gc]);
+        if (p.out_bf16) p.out_bf16[grow * p.ld_out + gc] = __float2bfloat16(x);
+        if (p.out_f32) {
+            if (p.accumulate) atomicAdd(p.out_f32 + grow * p.ld_f32 + gc, x);
+            else p.out_f32[grow * p.ld_f32 + gc] = x;
+        }
+    }
+}
+
+// One accumulator tile (this warp's 32 rows x every other 32-column chunk) through the fused epilogue.
+// EX: extra operand read by the epilogue (0 none, 1 bf16 residual or dGELU aux, 2 fp32 residual).  Chunks go in
+// groups of two: the group's operand loads are issued together (for the first group: before the accumulator is
+// complete, so they fly while the MMAs of the tile still run), then each chunk is processed 16 columns at a
+// time, which keeps the live registers low enough that nothing spills (local memory has no L1 behind it here:
+// the shared-memory carve-out is the whole 227 KB).
+template <int BLOCK_N, int EX, int CTAS>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc, int lane, int half, long long grow,
+                                              int ncol0, uint32_t tfull, uint32_t tfull_phase, uint32_t tempty) {
+    constexpr int MY = BLOCK_N / 64;                 // chunks per warp: 1, 2 or 4
+    constexpr int G = MY < 2 ? MY : 2;               // chunks per group
+    constexpr int W = EX == 2 ? 32 : 16;             // 32-bit words of the extra operand per chunk row
+    const bool row_ok = grow < p.M;
+    uint32_t pf[EX == 0 ? 1 : G * W];
+    const bf16* exb = p.residual ? p.residual : p.aux;
+    const long long ld_ex = p.residual ? p.ld_res : p.ld_aux;
+#pragma unroll 1
+    for (int g0 = 0; g0 < MY; g0 += G) {
+        if (EX != 0) {
+#pragma unroll
+            for (int ii = 0; ii < G; ++ii) {
+                const int col0 = ncol0 + (2 * (g0 + ii) + half) * EPI_COLS;
+                if (p.vec_ok && col0 + EPI_COLS <= p.N && row_ok) {
+                    const uint8_t* src = EX == 2
+                        ? reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(exb) + grow * ld_ex + col0)
+                        : reinterpret_cast<const uint8_t*>(exb + grow * ld_ex + col0);
+#pragma unroll
+                    for (int j = 0; j < W / 8; ++j) ptx::ldg256(src + 32 * j, pf + ii * W + 8 * j);
+                }
+            }
+        }
+        if (g0 == 0) {
+            ptx::mbar_wait(tfull, tfull_phase);
+            ptx::tc_fence_after();
+        }
+#pragma unroll
+        for (int ii = 0; ii < G; ++ii) {
+            const int c = 2 * (g0 + ii) + half;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col0 = ncol0 + c * EPI_COLS + h * 16;
+                uint32_t r[16];
+                ptx::tmem_ld_32x16(tacc + c * EPI_COLS + h * 16, r);
+                ptx::tmem_wait_ld();
+                if (g0 + ii == MY - 1 && h == 1) {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CTAS == 2) ptx::mbar_arrive_remote(tempty);
+                        else ptx::mbar_arrive(tempty);
+                    }
+                }
+                if (col0 >= p.N || !row_ok) continue;
+                const uint32_t* ex = pf + ii * W + h * (W / 2);
+                if (p.vec_ok && ncol0 + (c + 1) * EPI_COLS <= p.N) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        }
+                    }
+                    if (p.out_pre) store_bf16_row16(p.out_pre + grow * p.ld_pre + col0, v);
+                    if (p.act == UC2_ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+                    } else if (p.act == UC2_ACT_TANH) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fast_tanh(v[j]);
+                    } else if (p.act == UC2_ACT_DGELU) {
+                        if (EX == 1 && !p.residual) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 u = unpack_bf16(ex[j]);
+                                v[2 * j] *= gelu_erf_grad(u.x);
+                                v[2 * j + 1] *= gelu_erf_grad(u.y);
+                            }
+                        } else {
+                            // residual and aux together (not used by the encoder): aux fetched late
+                            const uint32_t* a = reinterpret_cast<const uint32_t*>(p.aux + grow * p.ld_aux + col0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 u = unpack_bf16(__ldg(a + j));
+                                v[2 * j] *= gelu_erf_grad(u.x);
+                                v[2 * j + 1] *= gelu_erf_grad(u.y);
+                            }
+                        }
+                    }
+                    if (EX == 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(ex[j]);
+                    } else if (EX == 1 && p.residual) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 u = unpack_bf16(ex[j]);
+                            v[2 * j] += u.x;
+                            v[2 * j + 1] += u.y;
+                        }
+                    }
+                    if (p.out_bf16) store_bf16_row16(p.out_bf16 + grow * p.ld_out + col0, v);
+                    if (p.out_f32) {
+                        float* dst = p.out_f32 + grow * p.ld_f32 + col0;
+                        if (p.accumulate) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                                             "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                                             : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                ptx::stg256(dst + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]),
+                                            __float_as_uint(v[8 * j + 2]), __float_as_uint(v[8 * j + 3]),
+                                            __float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]),
+                                            __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
+                        }
+                    }
+                } else {
+                    // ragged right edge or unaligned leading dimensions: scalar path (out of line, rolled up: it
+                    // runs for at most one chunk per row of tiles on the shapes of this model)
+                    float loc[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) loc[j] = __uint_as_float(r[j]);
+                    epilogue_scalar_row(p, loc, grow, col0);
+                }
+            }
+        }
+    }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
-    using C = Cfg<BLOCK_N>;
+    using C = Cfg<BLOCK_N, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES + STAGING_BYTES;
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
     // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
@@ -76,11 +245,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::STAGES + 4);
     volatile uint32_t* tmem_ptr_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + STAGING_BYTES +
-                                             8 * (2 * C::STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CTAS == 2 ? ptx::cluster_ctarank() : 0u;
+    const int unit = CTAS == 2 ? (blockIdx.x >> 1) : blockIdx.x;          // persistent worker (CTA or CTA pair)
+    const int num_units = CTAS == 2 ? (gridDim.x >> 1) : gridDim.x;
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -91,17 +262,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull_bar(a), 1);
-            ptx::mbar_init(tempty_bar(a), EPI_WARPS);   // one arrive per epilogue warp
+            ptx::mbar_init(tempty_bar(a), EPI_WARPS * CTAS);   // one arrive per epilogue warp of every CTA
         }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
     if (warp_idx == 1) {
-        ptx::tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (CTAS == 2) {
+            ptx::tmem_alloc_pair(tmem_ptr_addr, C::TMEM_COLS);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) ptx::cluster_sync();      // the peer's barriers must exist before anything signals them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -113,41 +290,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = unit; t < total_tiles; t += num_units) {
                 const int n_blk = t % p.num_n_blocks;
                 const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
                 const int split = t / tiles_mn;
                 const int kb0 = split * p.k_blocks_per_split;
                 const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+                const int m0 = (m_blk * CTAS + (int)cta_rank) * BLOCK_M;
+                const int n0 = n_blk * BLOCK_N + (int)cta_rank * C::B_ROWS;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                     const uint32_t sb = sa + C::A_BYTES;
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    // the pair's loads all report to the leader's barrier, which expects both CTAs' bytes
+                    const uint32_t fb = CTAS == 2 ? ptx::map_to_cta(full_bar(stage), 0) : full_bar(stage);
+                    if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES * CTAS);
+                    auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+                        if (CTAS == 2) ptx::tma_load_2d_pair(dst, m, fb, c0, c1);
+                        else ptx::tma_load_2d(dst, m, fb, c0, c1);
+                    };
                     if (!A_MN) {
-                        ptx::tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+                        load(sa, &tmap_a, kb * BLOCK_K, m0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BLOCK_M / 64; ++j)
-                            ptx::tma_load_2d(sa + j * 8192, &tmap_a, full_bar(stage), m_blk * BLOCK_M + j * 64,
-                                             kb * BLOCK_K);
+                        for (int j = 0; j < BLOCK_M / 64; ++j) load(sa + j * 8192, &tmap_a, m0 + j * 64, kb * BLOCK_K);
                     }
                     if (!B_MN) {
-                        ptx::tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+                        load(sb, &tmap_b, kb * BLOCK_K, n0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BLOCK_N / 64; ++j)
-                            ptx::tma_load_2d(sb + j * 8192, &tmap_b, full_bar(stage), n_blk * BLOCK_N + j * 64,
-                                             kb * BLOCK_K);
+                        for (int j = 0; j < C::B_ROWS / 64; ++j) load(sb + j * 8192, &tmap_b, n0 + j * 64, kb * BLOCK_K);
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp_idx == 1) {
-        // ===================================== MMA issuer =======================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::idesc_bf16_f32(BLOCK_M, BLOCK_N, A_MN, B_MN);
+        // ===================================== MMA issuer (leader CTA) ==========================
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = ptx::idesc_bf16_f32(BLOCK_M * CTAS, BLOCK_N, A_MN, B_MN);
             // K-major: 8-row groups 1024 B apart (SBO); MN-major: 64-element blocks 8192 B apart (LBO),
             // 8-k-row groups 1024 B apart (SBO)
             constexpr uint32_t A_LBO = A_MN ? 8192u : 16u, B_LBO = B_MN ? 8192u : 16u;
@@ -156,11 +337,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = unit; t < total_tiles; t += num_units) {
                 const int split = t / tiles_mn;
                 const int kb0 = split * p.k_blocks_per_split;
                 const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
-                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                if (CTAS == 2) ptx::mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+                else ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -172,12 +354,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         const uint64_t da = ptx::smem_desc_sw128(sa + k * A_KSTEP, A_LBO, 1024u);
                         const uint64_t db = ptx::smem_desc_sw128(sb + k * B_KSTEP, B_LBO, 1024u);
-                        ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+                        if (CTAS == 2) ptx::umma_bf16_pair(d_tmem, da, db, idesc, accum);
+                        else ptx::umma_bf16(d_tmem, da, db, idesc, accum);
                     }
-                    ptx::umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs retire
+                    // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+                    if (CTAS == 2) ptx::umma_commit_pair(empty_bar(stage));
+                    else ptx::umma_commit(empty_bar(stage));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
-                ptx::umma_commit(tfull_bar(acc));          // accumulator complete -> epilogue
+                // accumulator complete -> epilogue warps (of both CTAs)
+                if (CTAS == 2) ptx::umma_commit_pair(tfull_bar(acc));
+                else ptx::umma_commit(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -185,167 +373,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ===================================== epilogue =========================================
         const int q = warp_idx & 3;                       // TMEM lane quarter owned by this warp
         const int half = (warp_idx - 2) >> 2;             // which of the interleaved 32-column chunks
+        const int ex_kind = p.residual ? (p.res_f32 ? 2 : 1) : (p.act == UC2_ACT_DGELU ? 1 : 0);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = unit; t < total_tiles; t += num_units) {
             const int n_blk = t % p.num_n_blocks;
             const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
-            ptx::mbar_wait(tfull_bar(acc), acc_phase);
-            ptx::tc_fence_after();
-            const long long grow = (long long)m_blk * BLOCK_M + q * 32 + lane;
-            const bool row_ok = grow < p.M;
-            constexpr int MY_CHUNKS = BLOCK_N / EPI_COLS / 2;
-#pragma unroll 1
-            for (int i = 0; i < MY_CHUNKS; ++i) {
-                const int c = 2 * i + half;
-                const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * EPI_COLS,
-                                   r);
-                // operands of the fused epilogue, requested while the accumulator load is in flight
-                const bool vec = p.vec_ok && col0 + EPI_COLS <= p.N;       // warp-uniform
-                const bool live = row_ok && col0 < p.N;
-                uint4 ex[8];                                               // residual (fp32: 8 x 16 B, bf16: 4) or aux
-                if (vec && live) {
-                    if (p.residual) {
-                        if (p.res_f32) {
-                            const uint4* src = reinterpret_cast<const uint4*>(
-                                reinterpret_cast<const float*>(p.residual) + grow * p.ld_res + col0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) ex[j] = __ldg(src + j);
-                        } else {
-                            const uint4* src = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + col0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) ex[j] = __ldg(src + j);
-                        }
-                    } else if (p.act == UC2_ACT_DGELU) {
-                        const uint4* src = reinterpret_cast<const uint4*>(p.aux + grow * p.ld_aux + col0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) ex[j] = __ldg(src + j);
-                    }
-                }
-                ptx::tmem_wait_ld();
-                if (i == MY_CHUNKS - 1) {
-                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
-                }
-                if (!live) continue;
-                if (vec) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                        }
-                    }
-                    if (p.out_pre) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.out_pre + grow * p.ld_pre + col0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                    }
-                    if (p.act == UC2_ACT_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                    } else if (p.act == UC2_ACT_TANH) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-                    } else if (p.act == UC2_ACT_DGELU && !p.residual) {
-                        const uint32_t* a = reinterpret_cast<const uint32_t*>(ex);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float2 u = unpack_bf16(a[j]);
-                            v[2 * j] *= gelu_erf_grad(u.x);
-                            v[2 * j + 1] *= gelu_erf_grad(u.y);
-                        }
-                    } else if (p.act == UC2_ACT_DGELU) {
-                        // residual and aux together (not used by the encoder): aux fetched late
-                        const uint32_t* a = reinterpret_cast<const uint32_t*>(p.aux + grow * p.ld_aux + col0);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float2 u = unpack_bf16(__ldg(a + j));
-                            v[2 * j] *= gelu_erf_grad(u.x);
-                            v[2 * j + 1] *= gelu_erf_grad(u.y);
-                        }
-                    }
-                    if (p.residual) {
-                        if (p.res_f32) {
-                            const float* f = reinterpret_cast<const float*>(ex);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] += f[j];
-                        } else {
-                            const uint32_t* a = reinterpret_cast<const uint32_t*>(ex);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float2 u = unpack_bf16(a[j]);
-                                v[2 * j] += u.x;
-                                v[2 * j + 1] += u.y;
-                            }
-                        }
-                    }
-                    if (p.out_bf16) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld_out + col0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                    }
-                    if (p.out_f32) {
-                        float* dst = p.out_f32 + grow * p.ld_f32 + col0;
-                        if (p.accumulate) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
-                                             "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                                             : "memory");
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                reinterpret_cast<float4*>(dst)[j] =
-                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        }
-                    }
-                } else {
-                    // ragged right edge or unaligned leading dimensions: scalar path
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int gc = col0 + j;
-                        if (gc >= p.N) continue;
-                        float x = __uint_as_float(r[j]);
-                        if (p.bias) x += p.bias[gc];
-                        if (p.out_pre) p.out_pre[grow * p.ld_pre + gc] = __float2bfloat16(x);
-                        if (p.act != UC2_ACT_NONE) {
-                            const float a =
-                                p.act == UC2_ACT_DGELU ? __bfloat162float(p.aux[grow * p.ld_aux + gc]) : 0.f;
-                            x = apply_act(x, p.act, a);
-                        }
-                        if (p.residual)
-                            x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[grow * p.ld_res + gc]
-                                           : __bfloat162float(p.residual[grow * p.ld_res + gc]);
-                        if (p.out_bf16) p.out_bf16[grow * p.ld_out + gc] = __float2bfloat16(x);
-                        if (p.out_f32) {
-                            if (p.accumulate) atomicAdd(p.out_f32 + grow * p.ld_f32 + gc, x);
-                            else p.out_f32[grow * p.ld_f32 + gc] = x;
-                        }
-                    }
-                }
-            }
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+            const long long grow = (long long)(m_blk * CTAS + (int)cta_rank) * BLOCK_M + q * 32 + lane;
+            const int ncol0 = n_blk * BLOCK_N;
+            const uint32_t te = CTAS == 2 ? ptx::map_to_cta(tempty_bar(acc), 0) : tempty_bar(acc);
+            if (ex_kind == 0)
+                epilogue_tile<BLOCK_N, 0, CTAS>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
+            else if (ex_kind == 1)
+                epilogue_tile<BLOCK_N, 1, CTAS>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
+            else
+                epilogue_tile<BLOCK_N, 2, CTAS>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
     // ------------------------------------------- teardown -------------------------------------------
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) ptx::cluster_sync();      // neither CTA may exit while its peer can still touch its smem / TMEM
+    else __syncthreads();
     if (warp_idx == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+        if (CTAS == 2) ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -386,16 +441,43 @@ int make_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, 
     return UC2_OK;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
-    using C = Cfg<BLOCK_N>;
-    static_assert(C::STAGES >= 3, "pipeline too shallow");
-    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+// How many persistent workers (CTAs, or CTA pairs) the device can hold for one kernel instantiation.
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
+int worker_slots(cudaError_t* err) {
+    using C = Cfg<BLOCK_N, CTAS>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
+    static int slots = 0;
     std::call_once(once, [&] {
+        auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, CTAS>;
         attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        slots = num_sms();
+        if (CTAS == 2 && attr_err == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * (num_sms() / 2));
+            cfg.blockDim = dim3(GEMM_THREADS);
+            cfg.dynamicSmemBytes = C::SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) slots = n;
+            else { slots = num_sms() / 2; cudaGetLastError(); }
+        }
     });
+    *err = attr_err;
+    return slots;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
+int launch(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
+    using C = Cfg<BLOCK_N, CTAS>;
+    static_assert(C::STAGES >= 3, "pipeline too shallow");
+    static_assert(CTAS == 1 || C::B_ROWS % 64 == 0, "a CTA pair needs BLOCK_N >= 128");
+    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, CTAS>;
+    cudaError_t attr_err;
+    const int slots = worker_slots<BLOCK_N, A_MN, B_MN, CTAS>(&attr_err);
     UC2_REQUIRE(attr_err == cudaSuccess, UC2_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES,
                 cudaGetErrorString(attr_err));
     CUtensorMap ta, tb;
@@ -403,42 +485,63 @@ int launch(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
     if (!A_MN) rc = make_tmap(&ta, a.a, a.M, a.K, a.lda, BLOCK_M);
     else       rc = make_tmap(&ta, a.a, a.K, a.M, a.lda, BLOCK_K);
     if (rc) return rc;
-    if (!B_MN) rc = make_tmap(&tb, a.b, a.N, a.K, a.ldb, BLOCK_N);
+    if (!B_MN) rc = make_tmap(&tb, a.b, a.N, a.K, a.ldb, C::B_ROWS);
     else       rc = make_tmap(&tb, a.b, a.K, a.N, a.ldb, BLOCK_K);
     if (rc) return rc;
     const int total = p.num_m_blocks * p.num_n_blocks * p.split_k;
-    const int grid = total < num_sms() ? total : num_sms();
+    const int workers = total < slots ? total : slots;
     {
         ProfScope prof(stream, 0, 2.0 * a.M * a.N * a.K);
-        kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+        if (CTAS == 1) {
+            kern<<<workers, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * workers);
+            cfg.blockDim = dim3(GEMM_THREADS);
+            cfg.dynamicSmemBytes = C::SMEM_BYTES;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+        }
     }
     return check_last("gemm_bf16_kernel");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 int dispatch_major(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t s) {
-    if (!a.a_mn && !a.b_mn) return launch<BLOCK_N, false, false>(a, p, s);
-    if (!a.a_mn && a.b_mn) return launch<BLOCK_N, false, true>(a, p, s);
-    if (a.a_mn && a.b_mn) return launch<BLOCK_N, true, true>(a, p, s);
-    return launch<BLOCK_N, true, false>(a, p, s);
+    if (!a.a_mn && !a.b_mn) return launch<BLOCK_N, false, false, CTAS>(a, p, s);
+    if (!a.a_mn && a.b_mn) return launch<BLOCK_N, false, true, CTAS>(a, p, s);
+    if (a.a_mn && a.b_mn) return launch<BLOCK_N, true, true, CTAS>(a, p, s);
+    return launch<BLOCK_N, true, false, CTAS>(a, p, s);
 }
 
-// Fewest waves, then least padding waste; ties -> the larger tile (fewer B re-reads).
-int pick_block_n(int M, int N, int split_k) {
+// Tile shape: fewest rounds of the persistent workers, weighted by the tile's MMA time; CTA pairs are preferred
+// (a 128-row CTA re-reads B from L2 twice as often) whenever the problem has at least 256 rows.
+void pick_tile(int M, int N, int split_k, int want_bn, int want_ctas, int* bn_out, int* ctas_out) {
     const int sms = num_sms();
-    const int mb = (M + BLOCK_M - 1) / BLOCK_M;
     double best = 1e30;
-    int best_bn = 128;
-    const int cands[3] = {256, 128, 64};
-    for (int i = 0; i < 3; ++i) {
-        const int bn = cands[i];
-        const long long tiles = 1LL * mb * ((N + bn - 1) / bn) * split_k;
-        const long long waves = (tiles + sms - 1) / sms;
-        // per-tile cost ~ MMA time (prop. to bn) + fixed overhead; smaller N tiles pay relatively more
-        const double cost = waves * (bn + 24.0);
-        if (cost < best - 1e-9) { best = cost; best_bn = bn; }
+    int best_bn = 128, best_ctas = 1;
+    const int bns[3] = {256, 128, 64};
+    for (int ctas = 2; ctas >= 1; --ctas) {
+        if (want_ctas && ctas != want_ctas) continue;
+        if (ctas == 2 && M <= BLOCK_M && !want_ctas) continue;
+        for (int i = 0; i < 3; ++i) {
+            const int bn = bns[i];
+            if (want_bn && bn != want_bn) continue;
+            if (ctas == 2 && bn < 128) continue;
+            const int units = ctas == 2 ? sms / 2 : sms;
+            const long long tiles = 1LL * ((M + BLOCK_M * ctas - 1) / (BLOCK_M * ctas)) * ((N + bn - 1) / bn) * split_k;
+            const long long rounds = (tiles + units - 1) / units;
+            // per-tile cost ~ MMA time (prop. to bn) + fixed overhead; 128-row CTAs pay for their L2 traffic
+            const double cost = rounds * (bn + 24.0) * (ctas == 1 ? 1.3 : 1.0);
+            if (cost < best - 1e-9) { best = cost; best_bn = bn; best_ctas = ctas; }
+        }
     }
-    return best_bn;
+    *bn_out = best_bn;
+    *ctas_out = best_ctas;
 }
 
 }  // namespace
@@ -458,32 +561,37 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
                 a.ldb);
     UC2_REQUIRE(a.out_bf16 || a.out_f32, UC2_ERR_ARG, "uc2_gemm_bf16: no output");
     UC2_REQUIRE(a.act != UC2_ACT_DGELU || a.aux, UC2_ERR_ARG, "uc2_gemm_bf16: DGELU needs aux");
+    UC2_REQUIRE(a.block_n == 0 || a.block_n == 64 || a.block_n == 128 || a.block_n == 256, UC2_ERR_ARG,
+                "uc2_gemm_bf16: block_n must be 0/64/128/256");
+    UC2_REQUIRE(a.ctas >= 0 && a.ctas <= 2 && !(a.ctas == 2 && a.block_n == 64), UC2_ERR_ARG,
+                "uc2_gemm_bf16: ctas must be 0 (auto), 1 or 2 (2 needs block_n >= 128)");
     int split_k = a.split_k < 0 ? 1 : a.split_k;
+    const bool can_split = a.out_f32 && a.accumulate && !a.out_bf16 && !a.out_pre && !a.bias && !a.residual &&
+                           a.act == UC2_ACT_NONE;
+    int bn = 0, ctas = 0;
     if (split_k == 0) {
-        // auto: only meaningful for the atomic-accumulate (wgrad) form; fill the SMs with K splits
+        // auto: only meaningful for the atomic-accumulate (wgrad) form; fill the workers with K splits
         split_k = 1;
-        const bool can_split = a.out_f32 && a.accumulate && !a.out_bf16 && !a.out_pre && !a.bias && !a.residual &&
-                               a.act == UC2_ACT_NONE;
+        pick_tile(a.M, a.N, 1, a.block_n, a.ctas, &bn, &ctas);
         if (can_split) {
-            const int bn0 = a.block_n ? a.block_n : (a.N >= 256 ? 256 : (a.N >= 128 ? 128 : 64));
-            const long long tiles = 1LL * ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + bn0 - 1) / bn0);
+            const long long tiles = 1LL * ((a.M + BLOCK_M * ctas - 1) / (BLOCK_M * ctas)) * ((a.N + bn - 1) / bn);
             const int kblocks = (a.K + BLOCK_K - 1) / BLOCK_K;
-            const int sms = num_sms();
+            const int units = ctas == 2 ? num_sms() / 2 : num_sms();
             double best = 0.0;
             for (int s = 1; s <= 32 && kblocks / s >= 4; ++s) {
                 const long long t = tiles * s;
-                const double eff = (double)t / (double)(((t + sms - 1) / sms) * sms);
+                const double eff = (double)t / (double)(((t + units - 1) / units) * units);
                 if (eff > best + 0.03) { best = eff; split_k = s; }
             }
         }
+    } else {
+        pick_tile(a.M, a.N, split_k, a.block_n, a.ctas, &bn, &ctas);
     }
     if (split_k > 1)
-        UC2_REQUIRE(a.out_f32 && a.accumulate && !a.out_bf16 && !a.out_pre && !a.bias && !a.residual &&
-                        a.act == UC2_ACT_NONE,
-                    UC2_ERR_ARG, "uc2_gemm_bf16: split_k>1 requires accumulate into out_f32 only");
+        UC2_REQUIRE(can_split, UC2_ERR_ARG, "uc2_gemm_bf16: split_k>1 requires accumulate into out_f32 only");
     GemmParams p;
     p.M = a.M; p.N = a.N; p.K = a.K;
-    p.num_m_blocks = (a.M + BLOCK_M - 1) / BLOCK_M;
+    p.num_m_blocks = (a.M + BLOCK_M * ctas - 1) / (BLOCK_M * ctas);
     p.num_k_blocks = (a.K + BLOCK_K - 1) / BLOCK_K;
     p.split_k = split_k > p.num_k_blocks ? p.num_k_blocks : split_k;
     p.k_blocks_per_split = (p.num_k_blocks + p.split_k - 1) / p.split_k;
@@ -496,18 +604,20 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
     p.out_pre = static_cast<bf16*>(a.out_pre); p.ld_pre = a.ld_pre;
     p.out_f32 = a.out_f32; p.ld_f32 = a.ld_f32;
     p.accumulate = a.accumulate;
-    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    p.vec_ok = (!a.residual || (a.ld_res % (a.residual_f32 ? 4 : 8) == 0 && al16(a.residual))) &&
-               (!a.aux || (a.ld_aux % 8 == 0 && al16(a.aux))) &&
-               (!a.out_bf16 || (a.ld_out % 8 == 0 && al16(a.out_bf16))) &&
-               (!a.out_pre || (a.ld_pre % 8 == 0 && al16(a.out_pre))) &&
-               (!a.out_f32 || (a.ld_f32 % 4 == 0 && al16(a.out_f32))) && (!a.bias || al16(a.bias));
-    int bn = a.block_n;
-    if (bn == 0) bn = pick_block_n(a.M, a.N, p.split_k);
-    UC2_REQUIRE(bn == 64 || bn == 128 || bn == 256, UC2_ERR_ARG, "uc2_gemm_bf16: block_n must be 64/128/256");
+    // 256-bit row slices: 32-byte aligned bases, pitches that keep every row 32-byte aligned
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    p.vec_ok = (!a.residual || (a.ld_res % (a.residual_f32 ? 8 : 16) == 0 && al32(a.residual))) &&
+               (!a.aux || (a.ld_aux % 16 == 0 && al32(a.aux))) &&
+               (!a.out_bf16 || (a.ld_out % 16 == 0 && al32(a.out_bf16))) &&
+               (!a.out_pre || (a.ld_pre % 16 == 0 && al32(a.out_pre))) &&
+               (!a.out_f32 || (a.ld_f32 % 8 == 0 && al32(a.out_f32))) && (!a.bias || aligned16(a.bias));
     p.num_n_blocks = (a.N + bn - 1) / bn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (bn == 256) return dispatch_major<256>(a, p, s);
-    if (bn == 128) return dispatch_major<128>(a, p, s);
-    return dispatch_major<64>(a, p, s);
+    if (ctas == 2) {
+        if (bn == 256) return dispatch_major<256, 2>(a, p, s);
+        return dispatch_major<128, 2>(a, p, s);
+    }
+    if (bn == 256) return dispatch_major<256, 1>(a, p, s);
+    if (bn == 128) return dispatch_major<128, 1>(a, p, s);
+    return dispatch_major<64, 1>(a, p, s);
 }
