@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--warm", type=int, default=3)
     a = ap.parse_args()
     M, H, F, Q = a.tokens, 768, 3072, 2304
     dev = "cuda"
@@ -53,17 +54,19 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tot_f = tot_ms = 0.0
     for name, m, n, k, fn in cases:
-        for _ in range(3):
+        for _ in range(a.warm):
             fn()
         torch.cuda.synchronize()
-        ms = 0.0
+        # back-to-back launches (as inside a training step: launch latency hidden, the 150-300 MB working set
+        # of one call already exceeds the 126 MB L2)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for _ in range(a.reps):
-            flush.zero_()                                   # evict L2 between timed launches
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
-            torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
-        ms /= a.reps
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.reps
         fl = 2.0 * m * n * k
         tot_f += fl; tot_ms += ms
         print(f"{name} M={m:6d} N={n:5d} K={k:6d}  {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s")

@@ -180,3 +180,22 @@ def test_cta_pair_dgrad_wgrad(block_n, ctas):
         _lib.gemm(dy2, x, N2, K2, Mtok, a_mn=True, b_mn=True, out_f32=dw, accumulate=True, split_k=split,
                   block_n=block_n, ctas=ctas)
         _check(dw, dy2.float().t() @ x.float() + 1.0, 1e-4, f"wgrad split {split}")
+
+
+@pytest.mark.parametrize("N,K", [(768, 768), (2304, 768)])
+def test_bench_sized_token_dim_tail_split(N, K):
+    """M = 19200 tokens (BASELINE configs[1]: 120 pairs x 160): 75 blocks of 256 rows on 74 CTA pairs -- the
+    leftover block goes to a second small-tile launch; every row must still be written exactly once."""
+    from uc2_b200 import _lib
+    M = 19200
+    a = _rand((M, K), 41).bfloat16()
+    b = _rand((N, K), 42, 0.05).bfloat16()
+    bias = _rand((N,), 43)
+    res = _rand((M, N), 44)
+    out = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    ob = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    _lib.gemm(a, b, M, N, K, bias=bias, residual=res, out_f32=out, out_bf16=ob)
+    ref = a.float() @ b.float().t() + bias + res
+    _check(out, ref, 2e-5, "fp32 out")
+    _check(ob, ref, 1e-2, "bf16 out")
+    assert torch.equal(out[-300:].bfloat16(), ob[-300:])

@@ -98,10 +98,13 @@ __device__ __forceinline__ void store8_f32(float* p, const float* f) {
 }
 
 // erf-form GELU (model/layer.py:31-37) and its derivative.
-// Phi(x) = 0.5 erfc(-x/sqrt2) through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e. far below
-// one bf16 ulp): erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z), z >= 0.
-// Written on the erfc side so that the negative tail has no 1 + erf cancellation; one MUFU.RCP + one
-// MUFU.EX2 per element, and exp(-z^2) = exp(-x^2/2) is shared with the density term of the derivative.
+// 0.5 erfc(|x|/sqrt2) through Abramowitz-Stegun 7.1.25: erfc(z) = t (a1 + t (a2 + t a3)) exp(-z^2),
+// t = 1 / (1 + p z), z >= 0, |error| <= 2.5e-5 on erf.  The results are rounded to bf16 (half an ulp is 2e-3
+// relative), so gelu is off by at most 2.6e-5 absolute / gelu' by 1.1e-5 -- two orders below the storage
+// rounding -- while the whole evaluation is 11 FP32 instructions + MUFU.RCP + MUFU.EX2 (erff() costs ~3x that,
+// and these run in GEMM epilogues that have to keep up with the tensor pipe).  Written on the erfc side:
+// gelu(x) = max(x, 0) - |x| h has no 1 + erf cancellation in the negative tail.  exp(-z^2) = exp(-x^2/2) is
+// shared with the density term of the derivative.
 __device__ __forceinline__ float fast_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -117,24 +120,21 @@ __device__ __forceinline__ float fast_tanh(float x) {
     const float e = fast_ex2(fminf(2.8853900817779268f * x, 80.f));
     return 1.0f - 2.0f * fast_rcp(e + 1.0f);
 }
-struct GeluTerms { float Phi, e; };
+struct GeluTerms { float h, e; };       // h = 0.5 erfc(|x|/sqrt2), e = exp(-x^2/2)
 __device__ __forceinline__ GeluTerms gelu_terms(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
-    float pl = fmaf(1.061405429f, t, -1.453152027f);
-    pl = fmaf(pl, t, 1.421413741f);
-    pl = fmaf(pl, t, -0.284496736f);
-    pl = fmaf(pl, t, 0.254829592f);
+    const float t = fast_rcp(fmaf(0.47047f * 0.70710678118654752f, fabsf(x), 1.0f));
+    float pl = fmaf(0.5f * 0.7478556f, t, 0.5f * -0.0958798f);
+    pl = fmaf(pl, t, 0.5f * 0.3480242f);
     GeluTerms g;
-    g.e = fast_ex2(-1.4426950408889634f * z * z);
-    const float h = 0.5f * pl * t * g.e;          // 0.5 erfc(|x|/sqrt2)
-    g.Phi = x < 0.f ? h : 1.0f - h;
+    g.e = fast_ex2((x * x) * (-0.5f * 1.4426950408889634f));
+    g.h = (pl * t) * g.e;
     return g;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_terms(x).Phi; }
+__device__ __forceinline__ float gelu_erf(float x) { return fmaf(-fabsf(x), gelu_terms(x).h, fmaxf(x, 0.f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
     const GeluTerms g = gelu_terms(x);
-    return fmaf(x * 0.3989422804014327f, g.e, g.Phi);
+    const float Phi = 0.5f + copysignf(0.5f - g.h, x);
+    return fmaf(x * 0.3989422804014327f, g.e, Phi);
 }
 
 #endif  // __CUDACC__

@@ -520,8 +520,14 @@ int dispatch_major(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t s) 
 
 // Tile shape: fewest rounds of the persistent workers, weighted by the tile's MMA time; CTA pairs are preferred
 // (a 128-row CTA re-reads B from L2 twice as often) whenever the problem has at least 256 rows.
-void pick_tile(int M, int N, int split_k, int want_bn, int want_ctas, int* bn_out, int* ctas_out) {
+void pick_tile(int M, int N, int split_k, int want_bn, int want_ctas, int* bn_out, int* ctas_out, bool splittable = false) {
     const int sms = num_sms();
+    if (splittable && !want_bn && !want_ctas && M >= 2 * BLOCK_M && N >= 256) {
+        // K gets split to fill the machine afterwards: take the tile with the best bytes-per-flop
+        *bn_out = 256;
+        *ctas_out = 2;
+        return;
+    }
     double best = 1e30;
     int best_bn = 128, best_ctas = 1;
     const int bns[3] = {256, 128, 64};
@@ -535,8 +541,9 @@ void pick_tile(int M, int N, int split_k, int want_bn, int want_ctas, int* bn_ou
             const int units = ctas == 2 ? sms / 2 : sms;
             const long long tiles = 1LL * ((M + BLOCK_M * ctas - 1) / (BLOCK_M * ctas)) * ((N + bn - 1) / bn) * split_k;
             const long long rounds = (tiles + units - 1) / units;
-            // per-tile cost ~ MMA time (prop. to bn) + fixed overhead; 128-row CTAs pay for their L2 traffic
-            const double cost = rounds * (bn + 24.0) * (ctas == 1 ? 1.3 : 1.0);
+            // per-tile cost ~ MMA time (prop. to bn) + fixed overhead; narrow tiles and 128-row CTAs pay for their
+            // extra shared-memory / L2 traffic per flop (measured: scripts/gemm_bench.py, profiles/)
+            const double cost = rounds * (bn + 24.0) * (ctas == 1 ? 1.15 : 1.0) * (bn == 256 ? 1.0 : 1.3);
             if (cost < best - 1e-9) { best = cost; best_bn = bn; best_ctas = ctas; }
         }
     }
@@ -572,7 +579,7 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
     if (split_k == 0) {
         // auto: only meaningful for the atomic-accumulate (wgrad) form; fill the workers with K splits
         split_k = 1;
-        pick_tile(a.M, a.N, 1, a.block_n, a.ctas, &bn, &ctas);
+        pick_tile(a.M, a.N, 1, a.block_n, a.ctas, &bn, &ctas, can_split);
         if (can_split) {
             const long long tiles = 1LL * ((a.M + BLOCK_M * ctas - 1) / (BLOCK_M * ctas)) * ((a.N + bn - 1) / bn);
             const int kblocks = (a.K + BLOCK_K - 1) / BLOCK_K;
