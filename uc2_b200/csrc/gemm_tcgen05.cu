@@ -72,6 +72,38 @@ __device__ __forceinline__ void store_bf16_row16(bf16* dst, const float* v) {
                 pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
 }
 
+// Epilogue specialisation.  MODE 0 reads every switch from GemmParams at run time; MODE 1..7 are the seven
+// epilogues of the BertLayer stack with the switches fixed at compile time (no branches, a fraction of the code:
+// the epilogue warps were stalling on instruction fetch and uniform branches in the generic form).
+//   1 FFN1 forward   : + bias, pre-activation copy, erf-GELU            -> bf16
+//   2 FFN2 dgrad     : * gelu'(aux)                                      -> bf16
+//   3 O-proj / FFN2  : + bias + fp32 residual                            -> fp32
+//   4 QKV forward    : + bias                                            -> bf16
+//   5 FFN1/QKV dgrad : + bf16 residual                                   -> bf16
+//   6 wgrad          : fp32 atomic accumulate
+//   7 O-proj dgrad   : plain                                             -> bf16
+template <int MODE>
+struct Epi {
+    static __device__ __forceinline__ bool bias(const GemmParams& p) {
+        return MODE == 0 ? p.bias != nullptr : (MODE == 1 || MODE == 3 || MODE == 4);
+    }
+    static __device__ __forceinline__ bool out_pre(const GemmParams& p) { return MODE == 0 ? p.out_pre != nullptr : MODE == 1; }
+    static __device__ __forceinline__ int act(const GemmParams& p) {
+        return MODE == 0 ? p.act : (MODE == 1 ? UC2_ACT_GELU : (MODE == 2 ? UC2_ACT_DGELU : UC2_ACT_NONE));
+    }
+    static __device__ __forceinline__ bool residual(const GemmParams& p) {
+        return MODE == 0 ? p.residual != nullptr : (MODE == 3 || MODE == 5);
+    }
+    static __device__ __forceinline__ bool out_bf16(const GemmParams& p) {
+        return MODE == 0 ? p.out_bf16 != nullptr : (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 7);
+    }
+    static __device__ __forceinline__ bool out_f32(const GemmParams& p) {
+        return MODE == 0 ? p.out_f32 != nullptr : (MODE == 3 || MODE == 6);
+    }
+    static __device__ __forceinline__ bool accumulate(const GemmParams& p) { return MODE == 0 ? p.accumulate != 0 : MODE == 6; }
+    static constexpr int ex_kind = (MODE == 2 || MODE == 5) ? 1 : (MODE == 3 ? 2 : 0);   // meaningful for MODE != 0
+};
+
 __device__ __noinline__ void epilogue_scalar_row(const GemmParams& p, const float* acc, long long grow, int col0) {
 #pragma unroll 1
     for (int j = 0; j < 16; ++j) {
@@ -101,16 +133,17 @@ __device__ __noinline__ void epilogue_scalar_row(const GemmParams& p, const floa
 // complete, so they fly while the MMAs of the tile still run), then each chunk is processed 16 columns at a
 // time, which keeps the live registers low enough that nothing spills (local memory has no L1 behind it here:
 // the shared-memory carve-out is the whole 227 KB).
-template <int BLOCK_N, int EX, int CTAS>
+template <int BLOCK_N, int EX, int CTAS, int MODE>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc, int lane, int half, long long grow,
                                               int ncol0, uint32_t tfull, uint32_t tfull_phase, uint32_t tempty) {
+    using F = Epi<MODE>;
     constexpr int MY = BLOCK_N / 64;                 // chunks per warp: 1, 2 or 4
     constexpr int G = MY < 2 ? MY : 2;               // chunks per group
     constexpr int W = EX == 2 ? 32 : 16;             // 32-bit words of the extra operand per chunk row
     const bool row_ok = grow < p.M;
     uint32_t pf[EX == 0 ? 1 : G * W];
-    const bf16* exb = p.residual ? p.residual : p.aux;
-    const long long ld_ex = p.residual ? p.ld_res : p.ld_aux;
+    const bf16* exb = F::residual(p) ? p.residual : p.aux;
+    const long long ld_ex = F::residual(p) ? p.ld_res : p.ld_aux;
 #pragma unroll 1
     for (int g0 = 0; g0 < MY; g0 += G) {
         if (EX != 0) {
@@ -140,11 +173,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                 ptx::tmem_ld_32x16(tacc + c * EPI_COLS + h * 16, r);
                 ptx::tmem_wait_ld();
                 if (g0 + ii == MY - 1 && h == 1) {
-                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp (relaxed arrive:
+                    // nothing in generic memory is published here, and a release at cluster scope would make the
+                    // warp wait for all of its outstanding global stores)
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (CTAS == 2) ptx::mbar_arrive_remote(tempty);
+                        if (CTAS == 2) ptx::mbar_arrive_remote_relaxed(tempty);
                         else ptx::mbar_arrive(tempty);
                     }
                 }
@@ -154,22 +189,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias) {
+                    if (F::bias(p)) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
                             v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                         }
                     }
-                    if (p.out_pre) store_bf16_row16(p.out_pre + grow * p.ld_pre + col0, v);
-                    if (p.act == UC2_ACT_GELU) {
+                    if (F::out_pre(p)) store_bf16_row16(p.out_pre + grow * p.ld_pre + col0, v);
+                    if (F::act(p) == UC2_ACT_GELU) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-                    } else if (p.act == UC2_ACT_TANH) {
+                    } else if (F::act(p) == UC2_ACT_TANH) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fast_tanh(v[j]);
-                    } else if (p.act == UC2_ACT_DGELU) {
-                        if (EX == 1 && !p.residual) {
+                    } else if (F::act(p) == UC2_ACT_DGELU) {
+                        if (EX == 1 && !F::residual(p)) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float2 u = unpack_bf16(ex[j]);
@@ -190,7 +225,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                     if (EX == 2) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(ex[j]);
-                    } else if (EX == 1 && p.residual) {
+                    } else if (EX == 1 && F::residual(p)) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float2 u = unpack_bf16(ex[j]);
@@ -198,10 +233,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                             v[2 * j + 1] += u.y;
                         }
                     }
-                    if (p.out_bf16) store_bf16_row16(p.out_bf16 + grow * p.ld_out + col0, v);
-                    if (p.out_f32) {
+                    if (F::out_bf16(p)) store_bf16_row16(p.out_bf16 + grow * p.ld_out + col0, v);
+                    if (F::out_f32(p)) {
                         float* dst = p.out_f32 + grow * p.ld_f32 + col0;
-                        if (p.accumulate) {
+                        if (F::accumulate(p)) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
@@ -229,7 +264,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
     }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -373,7 +408,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ===================================== epilogue =========================================
         const int q = warp_idx & 3;                       // TMEM lane quarter owned by this warp
         const int half = (warp_idx - 2) >> 2;             // which of the interleaved 32-column chunks
-        const int ex_kind = p.residual ? (p.res_f32 ? 2 : 1) : (p.act == UC2_ACT_DGELU ? 1 : 0);
+        const int ex_kind = MODE != 0 ? Epi<MODE>::ex_kind
+                                      : (p.residual ? (p.res_f32 ? 2 : 1) : (p.act == UC2_ACT_DGELU ? 1 : 0));
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = unit; t < total_tiles; t += num_units) {
@@ -383,12 +419,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const long long grow = (long long)(m_blk * CTAS + (int)cta_rank) * BLOCK_M + q * 32 + lane;
             const int ncol0 = n_blk * BLOCK_N;
             const uint32_t te = CTAS == 2 ? ptx::map_to_cta(tempty_bar(acc), 0) : tempty_bar(acc);
-            if (ex_kind == 0)
-                epilogue_tile<BLOCK_N, 0, CTAS>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
+            if (MODE != 0)
+                epilogue_tile<BLOCK_N, Epi<MODE>::ex_kind, CTAS, MODE>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc),
+                                                                       acc_phase, te);
+            else if (ex_kind == 0)
+                epilogue_tile<BLOCK_N, 0, CTAS, 0>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
             else if (ex_kind == 1)
-                epilogue_tile<BLOCK_N, 1, CTAS>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
+                epilogue_tile<BLOCK_N, 1, CTAS, 0>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
             else
-                epilogue_tile<BLOCK_N, 2, CTAS>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
+                epilogue_tile<BLOCK_N, 2, CTAS, 0>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
@@ -442,14 +481,14 @@ int make_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, 
 }
 
 // How many persistent workers (CTAs, or CTA pairs) the device can hold for one kernel instantiation.
-template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS, int MODE>
 int worker_slots(cudaError_t* err) {
     using C = Cfg<BLOCK_N, CTAS>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     static int slots = 0;
     std::call_once(once, [&] {
-        auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, CTAS>;
+        auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, CTAS, MODE>;
         attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         slots = num_sms();
         if (CTAS == 2 && attr_err == cudaSuccess) {
@@ -470,14 +509,14 @@ int worker_slots(cudaError_t* err) {
     return slots;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS, int MODE = 0>
 int launch(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
     using C = Cfg<BLOCK_N, CTAS>;
     static_assert(C::STAGES >= 3, "pipeline too shallow");
     static_assert(CTAS == 1 || C::B_ROWS % 64 == 0, "a CTA pair needs BLOCK_N >= 128");
-    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, CTAS>;
+    auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, CTAS, MODE>;
     cudaError_t attr_err;
-    const int slots = worker_slots<BLOCK_N, A_MN, B_MN, CTAS>(&attr_err);
+    const int slots = worker_slots<BLOCK_N, A_MN, B_MN, CTAS, MODE>(&attr_err);
     UC2_REQUIRE(attr_err == cudaSuccess, UC2_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES,
                 cudaGetErrorString(attr_err));
     CUtensorMap ta, tb;
@@ -620,6 +659,26 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
                (!a.out_f32 || (a.ld_f32 % 8 == 0 && al32(a.out_f32))) && (!a.bias || aligned16(a.bias));
     p.num_n_blocks = (a.N + bn - 1) / bn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ctas == 2 && bn == 256 && p.vec_ok) {
+        // the BertLayer stack's own epilogues, compiled without run-time switches (see Epi<MODE>)
+        const bool bf = a.out_bf16 && !a.out_f32, f32o = a.out_f32 && !a.out_bf16;
+        const bool kk = !a.a_mn && !a.b_mn, kn = !a.a_mn && a.b_mn, nn = a.a_mn && a.b_mn;
+        const bool res32 = a.residual && a.residual_f32, resb = a.residual && !a.residual_f32;
+        if (kk && a.bias && a.out_pre && a.act == UC2_ACT_GELU && !a.residual && bf)
+            return launch<256, false, false, 2, 1>(a, p, s);
+        if (kn && !a.bias && !a.out_pre && a.act == UC2_ACT_DGELU && !a.residual && bf)
+            return launch<256, false, true, 2, 2>(a, p, s);
+        if (kk && a.bias && !a.out_pre && a.act == UC2_ACT_NONE && res32 && f32o && !a.accumulate)
+            return launch<256, false, false, 2, 3>(a, p, s);
+        if (kk && a.bias && !a.out_pre && a.act == UC2_ACT_NONE && !a.residual && bf)
+            return launch<256, false, false, 2, 4>(a, p, s);
+        if (kn && !a.bias && !a.out_pre && a.act == UC2_ACT_NONE && resb && bf)
+            return launch<256, false, true, 2, 5>(a, p, s);
+        if (nn && !a.bias && !a.out_pre && a.act == UC2_ACT_NONE && !a.residual && f32o && a.accumulate)
+            return launch<256, true, true, 2, 6>(a, p, s);
+        if (kn && !a.bias && !a.out_pre && a.act == UC2_ACT_NONE && !a.residual && bf)
+            return launch<256, false, true, 2, 7>(a, p, s);
+    }
     if (ctas == 2) {
         if (bn == 256) return dispatch_major<256, 2>(a, p, s);
         return dispatch_major<128, 2>(a, p, s);
