@@ -26,6 +26,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 from uc2_b200 import batch as UB  # noqa: E402
 from uc2_b200 import synth  # noqa: E402
@@ -302,6 +304,9 @@ def main():
             "attention_ms_per_step": ms_k[1],
             "attention_tflops": work_k[1] / (ms_k[1] * 1e-3) / 1e12 if ms_k[1] > 0 else 0.0, "traffic": None}
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     S = TXT + NBB
@@ -318,7 +323,7 @@ def main():
         line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                 "ms_per_step": ms,
                                 "sample": f"{n} pairs per step, 2 timed steps (oracle port of the reference step, fp32)"}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
