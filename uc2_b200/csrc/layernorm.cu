@@ -5,6 +5,7 @@
 // 12 layers; the bf16 copy of the output is the tensor-core operand of the next GEMM).
 // HBM-bound: one warp per row, 16/32-byte accesses.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace uc2 {
 namespace {
@@ -57,28 +58,73 @@ layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma
     }
 }
 
-// Each warp walks rows with a grid stride and keeps dgamma/dbeta/dbias partial sums in registers;
-// one shared-memory reduction and one global atomic per column per CTA at the end.
+// Backward.  Each warp walks rows with a grid stride and keeps dgamma/dbeta/dbias partial sums in registers
+// (72 accumulators + the row itself: ~150 registers, so only 8 warps fit on an SM).  Memory-level parallelism
+// therefore comes from a per-warp ring of LN_STAGES rows in shared memory filled by 1-D bulk copies
+// (cp.async.bulk, completion on an mbarrier per slot): 8 warps x 4 rows x 4.5 KB = 147 KB in flight per SM,
+// which is what it takes to keep HBM busy (the register-only version reached 1.9 TB/s).
+constexpr int LN_STAGES = 4;
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 template <bool F32>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 1)
 layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ gamma,
                      float eps, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dbias, long long rows) {
+    constexpr int XB = F32 ? HID * 4 : HID * 2;       // bytes of one x row
+    constexpr int SLOT = XB + HID * 2;                // x row + dy row
+    extern __shared__ __align__(128) uint8_t ln_smem[];
     __shared__ float red[3 * HID];
+    __shared__ __align__(8) unsigned long long bars[LN_WARPS * LN_STAGES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 3 * HID; i += blockDim.x) red[i] = 0.f;
+    const uint32_t ring = ptx::smem_u32(ln_smem) + warp * LN_STAGES * SLOT;
+    const uint32_t bar0 = ptx::smem_u32(bars) + warp * LN_STAGES * 8;
+    if (lane == 0) {
+        for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        ptx::fence_barrier_init();
+        ptx::fence_proxy_async();
+    }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * LN_WARPS;
+    const long long first = (long long)blockIdx.x * LN_WARPS + warp;
+    auto issue = [&](long long row, int s) {      // lane 0 only
+        ptx::mbar_arrive_expect_tx(bar0 + 8 * s, SLOT);
+        bulk_load(ring + s * SLOT, static_cast<const uint8_t*>(x) + row * XB, XB, bar0 + 8 * s);
+        bulk_load(ring + s * SLOT + XB, dy + row * HID, HID * 2, bar0 + 8 * s);
+    };
+    if (lane == 0)
+        for (int s = 0; s < LN_STAGES; ++s)
+            if (first + s * stride < rows) issue(first + s * stride, s);
     float g[VPL];
 #pragma unroll
     for (int i = 0; i < 3; ++i) load8_f32(gamma + col_of(lane, i), g + 8 * i);
     float ag[VPL], ab[VPL], ax[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) ag[i] = ab[i] = ax[i] = 0.f;
-    for (long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < rows;
-         row += (long long)gridDim.x * LN_WARPS) {
+    int s = 0;
+    uint32_t phase = 0;
+    for (long long row = first; row < rows; row += stride) {
+        ptx::mbar_wait(bar0 + 8 * s, phase);
         float v[VPL], d[VPL];
-        load_row<F32>(x, row, lane, v);
-        load_row<false>(dy, row, lane, d);
+        const uint8_t* slot = ln_smem + (warp * LN_STAGES + s) * SLOT;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (F32) load8_f32(reinterpret_cast<const float*>(slot) + col_of(lane, i), v + 8 * i);
+            else     load8_bf16(reinterpret_cast<const bf16*>(slot) + col_of(lane, i), v + 8 * i);
+            load8_bf16(reinterpret_cast<const bf16*>(slot + XB) + col_of(lane, i), d + 8 * i);
+        }
+        __syncwarp();                                  // every lane has its copy: the slot can be refilled
+        if (lane == 0 && row + LN_STAGES * stride < rows) {
+            ptx::fence_proxy_async();
+            issue(row + LN_STAGES * stride, s);
+        }
+        if (++s == LN_STAGES) { s = 0; phase ^= 1u; }
         float mean, rstd;
         stats(v, eps, mean, rstd);
         float s1 = 0.f, s2 = 0.f;
@@ -177,14 +223,18 @@ extern "C" UC2_API int uc2_layernorm_bwd(const void* x, int x_is_f32, const void
     UC2_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma), UC2_ERR_ARG,
                 "layernorm_bwd: pointers must be 16-byte aligned");
     long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
-    const long long cap = 4LL * num_sms();
+    const long long cap = num_sms();                  // one CTA per SM: the row ring takes most of its shared memory
     if (blocks > cap) blocks = cap;
-    if (x_is_f32)
-        layernorm_bwd_kernel<true><<<(unsigned)blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    const int smem = LN_WARPS * LN_STAGES * ((x_is_f32 ? HID * 4 : HID * 2) + HID * 2);
+    if (x_is_f32) {
+        UC2_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        layernorm_bwd_kernel<true><<<(unsigned)blocks, LN_WARPS * 32, smem, (cudaStream_t)stream>>>(
             x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows);
-    else
-        layernorm_bwd_kernel<false><<<(unsigned)blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    } else {
+        UC2_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        layernorm_bwd_kernel<false><<<(unsigned)blocks, LN_WARPS * 32, smem, (cudaStream_t)stream>>>(
             x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows);
+    }
     return check_last("layernorm_bwd_kernel");
 }
 
