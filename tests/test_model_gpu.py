@@ -74,6 +74,11 @@ def check_grads(g, tag, model, norm_rtol=3e-2, sample_rtol=0.1):
             assert got[0] < 1e-3 * biggest, (name, got[0])
             continue
         rel = abs(got[0] - ref[0]) / ref[0]
+        if params[name].numel() <= 2 and ref[0] < 1e-2 * biggest:
+            # a near-cancelling scalar (rank_output.bias: 1.8e-4 left over from terms of 6e-2): its RELATIVE error is
+            # bf16 forward noise amplified ~300x, so it gets the mixed absolute bound instead
+            assert abs(got[0] - ref[0]) <= 1e-3 * biggest, (name, got[0], ref[0])
+            continue
         if rel > worst[0]:
             worst = (rel, name)
         rms = ref[0] / np.sqrt(params[name].numel())

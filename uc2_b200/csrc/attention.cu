@@ -1,9 +1,13 @@
 // Flash-style key-padding-masked self-attention for 12 heads x 64 (forward + backward), S <= 512.
 // Replaces BertSelfAttention.forward model/layer.py:80-100 (scores, additive mask, softmax, P.V,
 // head merge) without materialising the two [B,12,S,S] tensors of the reference.
-// Round-1 implementation: warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate) with the whole K/V
-// (forward, dQ pass) or Q/dO (dK/dV pass) of one (batch, head) resident in shared memory; attention is
-// 3.4% of the encoder FLOPs at S=160, the tcgen05 port is tracked in DESIGN.md.
+// Warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate); attention is 3.4% of the encoder FLOPs at S=160
+// (SURVEY 8d).  Two generations of kernels live here:
+//   * S <= 256 (every BASELINE shape): one CTA per (batch, head) with Q, K, V (and dO) of that head resident in
+//     shared memory ONCE, one warp per 16 rows, 32-wide inner chunks (so S = 160 costs 160, not 192, in both
+//     dimensions).  The backward kernel is persistent and double-buffers the next head's tiles with cp.async
+//     while it computes dQ (phase A, warp = 16 query rows) and dK/dV (phase B, warp = 16 key rows).
+//   * S <= 512: the tiled kernels (64-row query / key tiles per CTA) kept as the general path.
 #include "common.cuh"
 
 namespace uc2 {
@@ -344,6 +348,267 @@ attention_bwd_dkv_kernel(const bf16* __restrict__ qkv, const long long* __restri
     store_c_bf16(dqkv, QKV_LD, base + rl, 2 * HID + h * HD, lane, dv, S, rl);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// per-(batch, head) kernels for S <= 256
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KC = 32;            // inner chunk (keys in phase A / forward, queries in phase B)
+constexpr int BH_MAX_WARPS = 10;      // S = 160 -> one 16-row tile per warp
+
+__device__ __forceinline__ float ex2a(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// rows of a [*, ld] bf16 matrix (64 columns starting at col0) -> swizzled tile, any thread count
+__device__ __forceinline__ void load_tile_n(uint32_t smem, const bf16* g, long long ld, long long grow0, int col0,
+                                            int nrows, int valid_rows, int nthreads) {
+    for (int i = threadIdx.x; i < nrows * 8; i += nthreads) {
+        const int r = i >> 3, c = i & 7;
+        const bool ok = r < valid_rows;
+        const bf16* src = g + (grow0 + (ok ? r : 0)) * ld + col0 + c * 8;
+        cp_async16(smem + tile_off(r, c), src, ok);
+    }
+}
+
+// C[16 x 16 NP] += A[16 x 64(k)] * B^T, B tile rows n0.. are the n index ([n][k] row-major)
+template <int NP>
+__device__ __forceinline__ void mma_nk_t(float (*c)[4], const uint32_t a[4][4], uint32_t tile, int n0, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            uint32_t r[4];
+            ldsm_x4(tile + tile_off(n0 + p * 16 + (lane & 7) + ((lane >> 4) << 3), kk * 2 + ((lane >> 3) & 1)), r);
+            mma16816(c[2 * p], a[kk], r[0], r[1]);
+            mma16816(c[2 * p + 1], a[kk], r[2], r[3]);
+        }
+    }
+}
+
+// C[16 x 64(n)] += P[16 x 16 NK] * B, P = fp32 C-layout fragments, B tile rows k0.. are the k index ([k][n])
+template <int NK>
+__device__ __forceinline__ void mma_kn_t(float c[8][4], const float (*p)[4], uint32_t tile, int k0, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < NK; ++kk) {
+        uint32_t a[4];
+        a[0] = pack_bf16(p[2 * kk][0], p[2 * kk][1]);
+        a[1] = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
+        a[2] = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+        a[3] = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t r[4];
+            ldsm_x4_t(tile + tile_off(k0 + kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), q * 2 + (lane >> 4)), r);
+            mma16816(c[2 * q], a, r[0], r[1]);
+            mma16816(c[2 * q + 1], a, r[2], r[3]);
+        }
+    }
+}
+
+// grid (NH, B); block = NW warps; shared: [Q SP][K SP][V SP][mask bias SP floats], SP = S rounded up to 32
+__global__ void __launch_bounds__(BH_MAX_WARPS * 32, 2)
+attention_fwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mask, bf16* __restrict__ ctx,
+                        float* __restrict__ lse, int S, int SP) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const uint32_t sK = sQ + SP * 128;
+    const uint32_t sV = sK + SP * 128;
+    float* mbias = reinterpret_cast<float*>(smem + 3 * SP * 128);
+    const long long base = (long long)b * S;
+    load_tile_n(sQ, qkv, QKV_LD, base, h * HD, SP, S, blockDim.x);
+    load_tile_n(sK, qkv, QKV_LD, base, HID + h * HD, SP, S, blockDim.x);
+    load_tile_n(sV, qkv, QKV_LD, base, 2 * HID + h * HD, SP, S, blockDim.x);
+    for (int i = threadIdx.x; i < SP; i += blockDim.x)
+        mbias[i] = i < S ? (mask[base + i] != 0 ? 0.f : MASK_LOG2) : -INFINITY;
+    cp_async_wait_all();
+    __syncthreads();
+    const int t = lane & 3, g = lane >> 2;
+    for (int q0 = warp * 16; q0 < S; q0 += nw * 16) {
+        uint32_t qf[4][4];
+        load_a_frags(sQ, q0, lane, qf);
+        float o[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+        float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+        for (int kc = 0; kc < SP; kc += KC) {
+            float sc[4][4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+            mma_nk_t<2>(sc, qf, sK, kc, lane);
+            float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const float2 bb = *reinterpret_cast<const float2*>(mbias + kc + n * 8 + 2 * t);
+                sc[n][0] = fmaf(sc[n][0], SCALE_LOG2, bb.x); sc[n][1] = fmaf(sc[n][1], SCALE_LOG2, bb.y);
+                sc[n][2] = fmaf(sc[n][2], SCALE_LOG2, bb.x); sc[n][3] = fmaf(sc[n][3], SCALE_LOG2, bb.y);
+                mx_lo = fmaxf(mx_lo, fmaxf(sc[n][0], sc[n][1]));
+                mx_hi = fmaxf(mx_hi, fmaxf(sc[n][2], sc[n][3]));
+            }
+            mx_lo = quad_max(mx_lo); mx_hi = quad_max(mx_hi);
+            const float c_lo = ex2a(m_lo - mx_lo), c_hi = ex2a(m_hi - mx_hi);
+            m_lo = mx_lo; m_hi = mx_hi;
+            l_lo *= c_lo; l_hi *= c_hi;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                sc[n][0] = ex2a(sc[n][0] - m_lo); sc[n][1] = ex2a(sc[n][1] - m_lo);
+                sc[n][2] = ex2a(sc[n][2] - m_hi); sc[n][3] = ex2a(sc[n][3] - m_hi);
+                l_lo += sc[n][0] + sc[n][1]; l_hi += sc[n][2] + sc[n][3];
+            }
+#pragma unroll
+            for (int n = 0; n < 8; ++n) { o[n][0] *= c_lo; o[n][1] *= c_lo; o[n][2] *= c_hi; o[n][3] *= c_hi; }
+            mma_kn_t<2>(o, sc, sV, kc, lane);
+        }
+        l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
+        const float i_lo = 1.f / l_lo, i_hi = 1.f / l_hi;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { o[n][0] *= i_lo; o[n][1] *= i_lo; o[n][2] *= i_hi; o[n][3] *= i_hi; }
+        store_c_bf16(ctx, HID, base + q0, h * HD, lane, o, S, q0);
+        if (t == 0) {
+            float* L = lse + ((long long)b * NH + h) * S;
+            if (q0 + g < S) L[q0 + g] = (m_lo + log2f(l_lo)) * (1.f / LOG2E);
+            if (q0 + g + 8 < S) L[q0 + g + 8] = (m_hi + log2f(l_hi)) * (1.f / LOG2E);
+        }
+    }
+}
+
+// Persistent backward: grid = min(B * NH, #SMs) CTAs of NW warps looping over (batch, head) items.
+// shared per buffer: [Q SP][K SP][V SP][dO SP] tiles; then per CTA: lse2[SP], delta[SP], mbias[SP] floats.
+__global__ void __launch_bounds__(BH_MAX_WARPS * 32, 1)
+attention_bwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mask,
+                        const bf16* __restrict__ dctx, const float* __restrict__ lse,
+                        const float* __restrict__ delta, bf16* __restrict__ dqkv, int B, int S, int SP, int nbuf) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const int buf_bytes = 4 * SP * 128;
+    float* s_lse = reinterpret_cast<float*>(smem + nbuf * buf_bytes);
+    float* s_del = s_lse + SP;
+    float* s_mb = s_del + SP;
+    const int items = B * NH;
+    auto issue = [&](int item, int buf) {
+        const int b = item / NH, h = item % NH;
+        const long long base = (long long)b * S;
+        const uint32_t sb = s0 + buf * buf_bytes;
+        load_tile_n(sb, qkv, QKV_LD, base, h * HD, SP, S, blockDim.x);
+        load_tile_n(sb + SP * 128, qkv, QKV_LD, base, HID + h * HD, SP, S, blockDim.x);
+        load_tile_n(sb + 2 * SP * 128, qkv, QKV_LD, base, 2 * HID + h * HD, SP, S, blockDim.x);
+        load_tile_n(sb + 3 * SP * 128, dctx, HID, base, h * HD, SP, S, blockDim.x);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int t = lane & 3, g = lane >> 2;
+    int it = blockIdx.x, buf = 0;
+    if (it < items) issue(it, 0);
+    for (; it < items; it += gridDim.x) {
+        const int b = it / NH, h = it % NH;
+        const long long base = (long long)b * S;
+        const int nxt = it + gridDim.x;
+        if (nbuf == 2 && nxt < items) {
+            issue(nxt, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        {
+            const float* L = lse + ((long long)b * NH + h) * S;
+            const float* Dl = delta + ((long long)b * NH + h) * S;
+            for (int i = threadIdx.x; i < SP; i += blockDim.x) {
+                s_lse[i] = i < S ? L[i] * LOG2E : INFINITY;     // +inf: padded rows contribute exp2(-inf) = 0
+                s_del[i] = i < S ? Dl[i] : 0.f;
+                s_mb[i] = i < S ? (mask[base + i] != 0 ? 0.f : MASK_LOG2) : -INFINITY;
+            }
+        }
+        __syncthreads();
+        const uint32_t sQ = s0 + buf * buf_bytes, sK = sQ + SP * 128, sV = sK + SP * 128, sdO = sV + SP * 128;
+        // ---------------- phase A: dQ, warp = 16 query rows, loop over keys
+        for (int q0 = warp * 16; q0 < S; q0 += nw * 16) {
+            uint32_t qf[4][4], dof[4][4];
+            load_a_frags(sQ, q0, lane, qf);
+            load_a_frags(sdO, q0, lane, dof);
+            const float lse_lo = s_lse[q0 + g], lse_hi = s_lse[q0 + g + 8];
+            const float d_lo = s_del[q0 + g], d_hi = s_del[q0 + g + 8];
+            float dq[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+            for (int kc = 0; kc < SP; kc += KC) {
+                float sc[4][4], dp[4][4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+                    dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+                }
+                mma_nk_t<2>(sc, qf, sK, kc, lane);
+                mma_nk_t<2>(dp, dof, sV, kc, lane);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const float2 bb = *reinterpret_cast<const float2*>(s_mb + kc + n * 8 + 2 * t);
+                    const float p0 = ex2a(fmaf(sc[n][0], SCALE_LOG2, bb.x) - lse_lo);
+                    const float p1 = ex2a(fmaf(sc[n][1], SCALE_LOG2, bb.y) - lse_lo);
+                    const float p2 = ex2a(fmaf(sc[n][2], SCALE_LOG2, bb.x) - lse_hi);
+                    const float p3 = ex2a(fmaf(sc[n][3], SCALE_LOG2, bb.y) - lse_hi);
+                    sc[n][0] = p0 * (dp[n][0] - d_lo) * 0.125f; sc[n][1] = p1 * (dp[n][1] - d_lo) * 0.125f;
+                    sc[n][2] = p2 * (dp[n][2] - d_hi) * 0.125f; sc[n][3] = p3 * (dp[n][3] - d_hi) * 0.125f;
+                }
+                mma_kn_t<2>(dq, sc, sK, kc, lane);
+            }
+            store_c_bf16(dqkv, QKV_LD, base + q0, h * HD, lane, dq, S, q0);
+        }
+        // ---------------- phase B: dK, dV, warp = 16 key rows, loop over queries
+        for (int k0 = warp * 16; k0 < S; k0 += nw * 16) {
+            uint32_t kf[4][4], vf[4][4];
+            load_a_frags(sK, k0, lane, kf);
+            load_a_frags(sV, k0, lane, vf);
+            const float mb_lo = s_mb[k0 + g], mb_hi = s_mb[k0 + g + 8];
+            float dk[8][4], dv[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+                dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+            }
+            for (int qc = 0; qc < SP; qc += KC) {
+                float st[4][4], dpt[4][4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
+                    dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
+                }
+                mma_nk_t<2>(st, kf, sQ, qc, lane);        // S^T[key, q]
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const float2 ll = *reinterpret_cast<const float2*>(s_lse + qc + n * 8 + 2 * t);
+                    st[n][0] = ex2a(fmaf(st[n][0], SCALE_LOG2, mb_lo) - ll.x);
+                    st[n][1] = ex2a(fmaf(st[n][1], SCALE_LOG2, mb_lo) - ll.y);
+                    st[n][2] = ex2a(fmaf(st[n][2], SCALE_LOG2, mb_hi) - ll.x);
+                    st[n][3] = ex2a(fmaf(st[n][3], SCALE_LOG2, mb_hi) - ll.y);
+                }
+                mma_kn_t<2>(dv, st, sdO, qc, lane);       // dV += P^T dO
+                mma_nk_t<2>(dpt, vf, sdO, qc, lane);      // dP^T[key, q]
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const float2 ee = *reinterpret_cast<const float2*>(s_del + qc + n * 8 + 2 * t);
+                    st[n][0] *= (dpt[n][0] - ee.x) * 0.125f; st[n][1] *= (dpt[n][1] - ee.y) * 0.125f;
+                    st[n][2] *= (dpt[n][2] - ee.x) * 0.125f; st[n][3] *= (dpt[n][3] - ee.y) * 0.125f;
+                }
+                mma_kn_t<2>(dk, st, sQ, qc, lane);        // dK += dS^T Q
+            }
+            store_c_bf16(dqkv, QKV_LD, base + k0, HID + h * HD, lane, dk, S, k0);
+            store_c_bf16(dqkv, QKV_LD, base + k0, 2 * HID + h * HD, lane, dv, S, k0);
+        }
+        __syncthreads();          // everyone is done with this buffer and the float arrays
+        if (nbuf == 1 && nxt < items) issue(nxt, 0);     // single buffer (S > 208): the reload is not overlapped
+        buf ^= (nbuf == 2);
+    }
+}
+
+// warps per CTA for the per-head kernels: every warp gets the same number of 16-row tiles
+int bh_warps(int S) {
+    const int tiles = (S + 15) / 16;
+    const int rounds = (tiles + BH_MAX_WARPS - 1) / BH_MAX_WARPS;
+    return (tiles + rounds - 1) / rounds;
+}
+
 int attn_check(int B, int S, int* S_pad) {
     UC2_REQUIRE(B > 0 && S > 0, UC2_ERR_ARG, "attention: bad shape B=%d S=%d", B, S);
     UC2_REQUIRE(S <= 512, UC2_ERR_UNSUPPORTED, "attention: S=%d > 512 (max_position_embeddings cap)", S);
@@ -369,9 +634,17 @@ extern "C" UC2_API int uc2_attention_fwd(const void* qkv, const long long* attn_
     UC2_REQUIRE(aligned16(qkv) && aligned16(ctx), UC2_ERR_ARG, "attention_fwd: qkv/ctx must be 16-byte aligned");
     int S_pad;
     if (int rc = attn_check(B, S, &S_pad)) return rc;
+    ProfScope prof((cudaStream_t)stream, 1, 4.0 * B * NH * (double)S * S * HD);
+    if (S <= 256) {
+        const int SP = (S + 31) / 32 * 32;
+        const int smem_bh = 3 * SP * 128 + SP * 4;
+        if (int rc = set_smem(attention_fwd_bh_kernel, smem_bh)) return rc;
+        attention_fwd_bh_kernel<<<dim3(NH, B), bh_warps(S) * 32, smem_bh, (cudaStream_t)stream>>>(
+            (const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, SP);
+        return check_last("attention_fwd_bh_kernel");
+    }
     const int smem = TILE * 128 + 2 * S_pad * 128 + S_pad * 4;
     if (int rc = set_smem(attention_fwd_kernel, smem)) return rc;
-    ProfScope prof((cudaStream_t)stream, 1, 4.0 * B * NH * (double)S * S * HD);
     attention_fwd_kernel<<<dim3(S_pad / TILE, NH, B), ATT_THREADS, smem, (cudaStream_t)stream>>>(
         (const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, S_pad);
     return check_last("attention_fwd_kernel");
@@ -391,6 +664,17 @@ extern "C" UC2_API int uc2_attention_bwd(const void* qkv, const long long* attn_
     ProfScope prof(s, 1, 10.0 * B * NH * (double)S * S * HD);      // 5 S x S x 64 products (7 computed)
     attention_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>((const bf16*)ctx, (const bf16*)dctx, delta_ws, B, S);
     if (int rc = check_last("attention_delta_kernel")) return rc;
+    if (S <= 256) {
+        const int SP = (S + 31) / 32 * 32;
+        const int nbuf = (2 * 4 * SP * 128 + 3 * SP * 4 <= 220 * 1024) ? 2 : 1;
+        const int smem_bh = nbuf * 4 * SP * 128 + 3 * SP * 4;
+        if (int rc = set_smem(attention_bwd_bh_kernel, smem_bh)) return rc;
+        const int items = B * NH;
+        const int grid = items < num_sms() ? items : num_sms();
+        attention_bwd_bh_kernel<<<grid, bh_warps(S) * 32, smem_bh, s>>>((const bf16*)qkv, attn_mask, (const bf16*)dctx,
+                                                                       lse, delta_ws, (bf16*)dqkv, B, S, SP, nbuf);
+        return check_last("attention_bwd_bh_kernel");
+    }
     const int smem_dq = 2 * TILE * 128 + 2 * S_pad * 128 + S_pad * 4;
     const int smem_dkv = 2 * TILE * 128 + 2 * S_pad * 128 + 2 * S_pad * 4;
     if (int rc = set_smem(attention_bwd_dq_kernel, smem_dq)) return rc;
