@@ -88,3 +88,16 @@ def sample_rows(S):
 
 def to_np(x):
     return x.detach().cpu().float().numpy().copy() if torch.is_tensor(x) else np.asarray(x)
+
+
+def retrieval_case(n_img=10, caps_per_img=2, seed=21, vocab=SMALL_VOCAB, family="vlxlmr"):
+    """A small retrieval evaluation set: images with ragged box counts, `caps_per_img` captions each
+    (caption c belongs to image c // caps_per_img), as ItmEvalDataset presents them (data/itm.py:891-902)."""
+    imgs = _items(n_img, seed, vocab, family, txt_range=(4, 4), bb_range=(10, 36))
+    caps = _items(n_img * caps_per_img, seed + 1, vocab, family, txt_range=(5, 16), bb_range=(10, 10))
+    images = [dict(img_feat=it["img_feat"], img_pos_feat=it["img_pos_feat"], id=f"img{i}") for i, it in enumerate(imgs)]
+    captions = [it["input_ids"] for it in caps]
+    txt_ids = [f"txt{i}" for i in range(len(captions))]
+    txt2img = {t: f"img{i // caps_per_img}" for i, t in enumerate(txt_ids)}
+    img2txts = {f"img{j}": [txt_ids[j * caps_per_img + k] for k in range(caps_per_img)] for j in range(n_img)}
+    return images, captions, txt_ids, txt2img, img2txts

@@ -220,7 +220,62 @@ def case_adamw():
     return out
 
 
+def case_retrieval():
+    """Retrieval scoring + recall: the reference model scores every (caption, image) pair through batches built
+    the way ItmValDataset.get_batch does (data/itm.py:456-485: one caption x a chunk of images sorted by box
+    count, reference pad_tensors / get_gather_index), stored as the fp16 score matrix of itm.py:515-538, and the
+    reference's own itm_eval (eval/itm.py) turns it -- and a larger random matrix -- into recall numbers."""
+    out = {}
+    cfg = cases.config(2)
+    sd = cases.weights(cfg, "retrieval")
+    m = build("retrieval", cfg, "vlxlmr", sd)
+    images, captions, txt_ids, txt2img, img2txts = cases.retrieval_case()
+    order = sorted(range(len(images)), key=lambda i: images[i]["img_feat"].size(0))
+    img_ids = [images[i]["id"] for i in order]
+    bs = 4
+    score = torch.zeros(len(captions), len(images), dtype=torch.float16)
+    with torch.no_grad():
+        for ci, ids in enumerate(captions):
+            j = 0
+            for st in range(0, len(order), bs):
+                sel = order[st:st + bs]
+                nbs = [images[i]["img_feat"].size(0) for i in sel]
+                tl = ids.numel()
+                input_ids = ids.unsqueeze(0).expand(len(sel), -1).clone()
+                img_feat = R.data.pad_tensors([images[i]["img_feat"] for i in sel], nbs)
+                img_pos = R.data.pad_tensors([images[i]["img_pos_feat"] for i in sel], nbs)
+                attn = torch.zeros(len(sel), max(nbs) + tl).long()
+                for k, nb in enumerate(nbs):
+                    attn.data[k, :tl + nb].fill_(1)
+                gi = R.data.get_gather_index([tl] * len(sel), nbs, len(sel), tl, attn.size(1))
+                batch = dict(input_ids=input_ids, position_ids=None, img_feat=img_feat, img_pos_feat=img_pos,
+                             attn_masks=attn, gather_index=gi)
+                sc = m(batch, compute_loss=False)
+                score[ci, j:j + len(sel)] = sc.squeeze(1).half()
+                j += len(sel)
+    out["retrieval|scores"] = score.float().numpy()
+    out["retrieval|img_order"] = np.array(order)
+    log = R.eval_itm.itm_eval(score.float(), txt_ids, img_ids, txt2img, img2txts)
+    out["retrieval|recall"] = np.array([log[k] for k in sorted(log)])
+    # recall on a larger random matrix (60 captions x 15 images, 4 captions per image)
+    n_img, cpi = 15, 4
+    big = torch.from_numpy(cases.synth.det_normal((n_img * cpi, n_img), 4242)).float()
+    tids = [f"t{i}" for i in range(n_img * cpi)]
+    iids = [f"i{j}" for j in range(n_img)]
+    t2i = {t: f"i{i // cpi}" for i, t in enumerate(tids)}
+    i2t = {f"i{j}": [tids[j * cpi + k] for k in range(cpi)] for j in range(n_img)}
+    for j in range(n_img):                      # make the ground truth partly retrievable
+        for k in range(cpi):
+            big[j * cpi + k, j] += 1.5 * ((j + k) % 3)
+    log2 = R.eval_itm.itm_eval(big, tids, iids, t2i, i2t)
+    out["recall|matrix"] = big.numpy()
+    out["recall|values"] = np.array([log2[k] for k in sorted(log2)])
+    out["recall|keys"] = np.array(sorted(log2))
+    return out
+
+
 CASES = {
+    "retrieval": case_retrieval,
     "pretrain": lambda: case_pretrain("vlxlmr"),
     "pretrain_uniter": lambda: case_pretrain("uniter"),
     "rank": lambda: case_rank("vlxlmr"),

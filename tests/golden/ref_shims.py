@@ -67,5 +67,9 @@ def load():
     import data.data as dd
     import data.itm as di
     import data.mrm as dm
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_eval_itm", REF + "/eval/itm.py")
+    ev = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ev)
     return types.SimpleNamespace(model=mm, itm=mi, ot=mo, layer=ml, adamw=oa, misc=om, sched=osch,
-                                 data=dd, data_itm=di, data_mrm=dm)
+                                 data=dd, data_itm=di, data_mrm=dm, eval_itm=ev)

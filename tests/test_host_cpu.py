@@ -165,3 +165,22 @@ def test_data_parallel_logic_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_recall_eval_matches_reference(golden):
+    """uc2_b200.retrieval.itm_eval (vectorised) against eval/itm.py run on the same matrices (tests/golden/retrieval.npz)."""
+    from uc2_b200.retrieval import itm_eval
+    g = golden("retrieval")
+    n_img, cpi = 15, 4
+    tids = [f"t{i}" for i in range(n_img * cpi)]
+    iids = [f"i{j}" for j in range(n_img)]
+    t2i = {t: f"i{i // cpi}" for i, t in enumerate(tids)}
+    i2t = {f"i{j}": [tids[j * cpi + k] for k in range(cpi)] for j in range(n_img)}
+    log = itm_eval(torch.from_numpy(g["recall|matrix"]), tids, iids, t2i, i2t)
+    assert sorted(log) == list(g["recall|keys"])
+    np.testing.assert_allclose([log[k] for k in sorted(log)], g["recall|values"], rtol=0, atol=1e-12)
+    # and on the score matrix the reference model produced for the small retrieval case
+    images, captions, txt_ids, txt2img, img2txts = cases.retrieval_case()
+    img_ids = [images[i]["id"] for i in g["retrieval|img_order"]]
+    log = itm_eval(torch.from_numpy(g["retrieval|scores"]), txt_ids, img_ids, txt2img, img2txts)
+    np.testing.assert_allclose([log[k] for k in sorted(log)], g["retrieval|recall"], rtol=0, atol=1e-12)

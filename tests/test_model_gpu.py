@@ -250,3 +250,32 @@ def test_no_cpu_path():
     m = itm.VLXLMRForImageTextRetrieval(cfg, 2048)
     with pytest.raises(RuntimeError):
         m(cases.batch_rank(), compute_loss=False)
+
+
+def test_retrieval_scoring_and_ranking(golden):
+    """uc2_b200.retrieval.inference (device-resident image chunks, caption side built on the GPU) against the
+    reference model's fp16 score matrix for every (caption, image) pair; rankings identical wherever the
+    reference's own scores are separated by more than the bf16 tolerance."""
+    from uc2_b200 import retrieval
+    g = golden("retrieval")
+    cfg = cases.config(2)
+    m, _ = build("retrieval", cfg)
+    images, captions, txt_ids, txt2img, img2txts = cases.retrieval_case()
+    arena = retrieval.ImageArena(images, mini_batch_size=4, device="cuda")
+    assert arena.order == list(g["retrieval|img_order"])
+    sm = retrieval.inference(m, captions, arena, rank=0, world=1)
+    assert sm.dtype == torch.float16 and tuple(sm.shape) == (len(captions), len(images))
+    ref = g["retrieval|scores"]
+    got = sm.float().cpu().numpy()
+    np.testing.assert_allclose(got, ref, atol=HID_TOL)
+    for r in range(ref.shape[0]):
+        order_ref = np.argsort(-ref[r], kind="stable")
+        order_got = np.argsort(-got[r], kind="stable")
+        for a, b_ in zip(order_ref, order_got):
+            assert a == b_ or abs(ref[r, a] - ref[r, b_]) <= 2 * HID_TOL, (r, order_ref, order_got)
+    # rows sharded over two "ranks" concatenate to the same matrix (itm.py:498 allgather order)
+    s0 = retrieval.inference(m, captions, arena, rank=0, world=2)
+    s1 = retrieval.inference(m, captions, arena, rank=1, world=2)
+    assert torch.equal(s0, sm[0::2]) and torch.equal(s1, sm[1::2])
+    log = retrieval.itm_eval(sm.float(), txt_ids, arena.img_ids, txt2img, img2txts)
+    assert set(log) == {"txt_r1", "txt_r5", "txt_r10", "txt_r_mean", "img_r1", "img_r5", "img_r10", "img_r_mean", "r_mean"}

@@ -137,3 +137,55 @@ def to_device(batch, device, non_blocking=True):
         else:
             out[k] = v
     return out
+
+
+class Prefetcher(object):
+    """data/loader.py:75-135 (PrefetchLoader): copies the NEXT batch host->device on a side stream while the
+    current step computes.  Batches must be pinned for the copy to overlap; every tensor is tied to the consuming
+    stream with record_stream (loader.py:120-134) so the caching allocator does not reuse it early."""
+
+    def __init__(self, loader, device):
+        self.loader = loader
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _preload(self, it):
+        try:
+            host = next(it)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(self.stream):
+            return self._move(host)
+
+    def _move(self, b):
+        if torch.is_tensor(b):
+            return b.to(self.device, non_blocking=True)
+        if isinstance(b, dict):
+            return {k: self._move(v) for k, v in b.items()}
+        if isinstance(b, (list, tuple)):
+            return type(b)(self._move(v) for v in b)
+        return b
+
+    def _record(self, b, stream):
+        if torch.is_tensor(b):
+            b.record_stream(stream)
+        elif isinstance(b, dict):
+            for v in b.values():
+                self._record(v, stream)
+        elif isinstance(b, (list, tuple)):
+            for v in b:
+                self._record(v, stream)
+
+    def __iter__(self):
+        it = iter(self.loader)
+        nxt = self._preload(it)
+        while nxt is not None:
+            cur_stream = torch.cuda.current_stream(self.device)
+            cur_stream.wait_stream(self.stream)
+            batch = nxt
+            self._record(batch, cur_stream)
+            nxt = self._preload(it)
+            yield batch
