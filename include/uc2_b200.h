@@ -57,6 +57,7 @@ UC2_API int uc2_profile_collect(double* ms_by_kind, double* work_by_kind, int* l
  *   if act == UC2_ACT_GELU : acc = gelu_erf(acc)          (model/layer.py:31-37)
  *   if act == UC2_ACT_DGELU: acc *= gelu_erf'(aux[m,n])   (backward of the above; aux = pre-act)
  *   if act == UC2_ACT_TANH : acc = tanh(acc)              (model/layer.py:184)
+ *   if drop_thresh : acc = keep(m,n) ? acc * drop_scale : 0  -- nn.Dropout before the residual add
  *   acc += residual[m,n] (bf16, or fp32 when residual_f32) -- BertSelfOutput / BertOutput residual
  *   out_bf16[m,n] = bf16(acc)  and/or  out_f32[m,n] (= or +=, see accumulate) acc
  * split_k > 1 splits K over CTAs and atomically accumulates into out_f32 (requires accumulate=1,
@@ -83,6 +84,10 @@ typedef struct {
     int block_n;      /* 0 = auto; else 64, 128 or 256 */
     int residual_f32; /* residual points at fp32 (the fp32 residual stream of the encoder) instead of bf16 */
     int ctas;         /* 0 = auto; 1 = one CTA per 128-row tile; 2 = CTA pair (cta_group::2) per 256-row tile */
+    /* dropout on (acc + bias) after the activation and before the residual add: nn.Dropout of BertSelfOutput /
+     * BertOutput (model/layer.py:113, 154).  keep(m, n) <=> (lowbias32((m * N + n) ^ drop_key) >> 16) >= drop_thresh;
+     * kept values are multiplied by drop_scale.  drop_thresh = 0 disables it (uc2_b200/dropout.py has the rules). */
+    unsigned int drop_key; unsigned int drop_thresh; float drop_scale;
 } uc2_gemm_args;
 
 UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream);
@@ -153,6 +158,12 @@ UC2_API int uc2_layernorm_fwd(const void* x, int x_is_f32, const float* gamma, c
                               void* y_bf16, float* y_f32, long long rows, void* stream);
 UC2_API int uc2_layernorm_bwd(const void* x, int x_is_f32, const void* dy, const float* gamma, float eps, void* dx,
                               float* dgamma, float* dbeta, float* dbias, long long rows, void* stream);
+/* Same, for x = dropout(dense) + residual (training): also writes dx_masked = keep ? dx * drop_scale : 0 (the gradient
+ * the dense branch sees; element index row * 768 + col under drop_key) and takes dbias from the masked gradient. */
+UC2_API int uc2_layernorm_bwd_dropout(const void* x, int x_is_f32, const void* dy, const float* gamma, float eps,
+                                      void* dx, float* dgamma, float* dbeta, float* dbias, long long rows,
+                                      void* dx_masked, unsigned int drop_key, unsigned int drop_thresh,
+                                      float drop_scale, void* stream);
 /* out[c] += sum_r x[r, c] for bf16 x [rows, cols] with leading dimension ld (bias gradients) */
 UC2_API int uc2_colsum_bf16(const void* x, long long ld, long long rows, int cols, float* out, void* stream);
 
@@ -169,6 +180,15 @@ UC2_API int uc2_attention_fwd(const void* qkv, const long long* attn_mask, void*
 /* dqkv: bf16 [B*S, 2304] (fully overwritten). delta_ws: fp32 [B,12,S] scratch. */
 UC2_API int uc2_attention_bwd(const void* qkv, const long long* attn_mask, const void* ctx, const void* dctx,
                               const float* lse, float* delta_ws, void* dqkv, int B, int S, void* stream);
+
+/* Training forms with attention-probability dropout (model/layer.py:94): P is dropped and rescaled after the
+ * softmax normalisation; element (q, k) of (batch b, head h) is kept iff
+ * (lowbias32((q * S + k) ^ drop_head_key(drop_key, b * 12 + h)) >> 16) >= drop_thresh.  S <= 256. */
+UC2_API int uc2_attention_fwd_dropout(const void* qkv, const long long* attn_mask, void* ctx, float* lse, int B, int S,
+                                      unsigned int drop_key, unsigned int drop_thresh, float drop_scale, void* stream);
+UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long long* attn_mask, const void* ctx, const void* dctx,
+                                      const float* lse, float* delta_ws, void* dqkv, int B, int S,
+                                      unsigned int drop_key, unsigned int drop_thresh, float drop_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The BertLayer stack: BertLayer.forward model/layer.py:159-170 applied num_hidden_layers times

@@ -409,7 +409,7 @@ __device__ __forceinline__ void mma_kn_t(float c[8][4], const float (*p)[4], uin
 // grid (NH, B); block = NW warps; shared: [Q SP][K SP][V SP][mask bias SP floats], SP = S rounded up to 32
 __global__ void __launch_bounds__(BH_MAX_WARPS * 32, 2)
 attention_fwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mask, bf16* __restrict__ ctx,
-                        float* __restrict__ lse, int S, int SP) {
+                        float* __restrict__ lse, int S, int SP, DropCfg drop) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int h = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -426,6 +426,7 @@ attention_fwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
     cp_async_wait_all();
     __syncthreads();
     const int t = lane & 3, g = lane >> 2;
+    const uint32_t hkey = drop_head_key(drop.key, b * NH + h);
     for (int q0 = warp * 16; q0 < S; q0 += nw * 16) {
         uint32_t qf[4][4];
         load_a_frags(sQ, q0, lane, qf);
@@ -459,6 +460,17 @@ attention_fwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
             }
 #pragma unroll
             for (int n = 0; n < 8; ++n) { o[n][0] *= c_lo; o[n][1] *= c_lo; o[n][2] *= c_hi; o[n][3] *= c_hi; }
+            if (drop.thresh) {
+                // attention-probability dropout (layer.py:94): the normaliser keeps every key, the dropped and
+                // rescaled probabilities only enter P.V
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t idx = (uint32_t)(q0 + g + (e >> 1) * 8) * (uint32_t)S + kc + n * 8 + 2 * t + (e & 1);
+                        sc[n][e] = drop_keep(hkey, idx, drop.thresh) ? sc[n][e] * drop.scale : 0.f;
+                    }
+            }
             mma_kn_t<2>(o, sc, sV, kc, lane);
         }
         l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
@@ -479,7 +491,8 @@ attention_fwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
 __global__ void __launch_bounds__(BH_MAX_WARPS * 32, 1)
 attention_bwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mask,
                         const bf16* __restrict__ dctx, const float* __restrict__ lse,
-                        const float* __restrict__ delta, bf16* __restrict__ dqkv, int B, int S, int SP, int nbuf) {
+                        const float* __restrict__ delta, bf16* __restrict__ dqkv, int B, int S, int SP, int nbuf,
+                        DropCfg drop) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
@@ -522,6 +535,7 @@ attention_bwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
         }
         __syncthreads();
         const uint32_t sQ = s0 + buf * buf_bytes, sK = sQ + SP * 128, sV = sK + SP * 128, sdO = sV + SP * 128;
+        const uint32_t hkey = drop_head_key(drop.key, b * NH + h);
         // ---------------- phase A: dQ, warp = 16 query rows, loop over keys
         for (int q0 = warp * 16; q0 < S; q0 += nw * 16) {
             uint32_t qf[4][4], dof[4][4];
@@ -548,6 +562,13 @@ attention_bwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
                     const float p1 = ex2a(fmaf(sc[n][1], SCALE_LOG2, bb.y) - lse_lo);
                     const float p2 = ex2a(fmaf(sc[n][2], SCALE_LOG2, bb.x) - lse_hi);
                     const float p3 = ex2a(fmaf(sc[n][3], SCALE_LOG2, bb.y) - lse_hi);
+                    if (drop.thresh) {        // dP = dropout'(dO V^T): same mask and scale as the forward pass
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t idx = (uint32_t)(q0 + g + (e >> 1) * 8) * (uint32_t)S + kc + n * 8 + 2 * t + (e & 1);
+                            dp[n][e] = drop_keep(hkey, idx, drop.thresh) ? dp[n][e] * drop.scale : 0.f;
+                        }
+                    }
                     sc[n][0] = p0 * (dp[n][0] - d_lo) * 0.125f; sc[n][1] = p1 * (dp[n][1] - d_lo) * 0.125f;
                     sc[n][2] = p2 * (dp[n][2] - d_hi) * 0.125f; sc[n][3] = p3 * (dp[n][3] - d_hi) * 0.125f;
                 }
@@ -583,15 +604,32 @@ attention_bwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
                     st[n][2] = ex2a(fmaf(st[n][2], SCALE_LOG2, mb_hi) - ll.x);
                     st[n][3] = ex2a(fmaf(st[n][3], SCALE_LOG2, mb_hi) - ll.y);
                 }
-                mma_kn_t<2>(dv, st, sdO, qc, lane);       // dV += P^T dO
                 mma_nk_t<2>(dpt, vf, sdO, qc, lane);      // dP^T[key, q]
+                uint32_t km = 0xFFFFu;                     // keep bits of this thread's 16 elements
+                if (drop.thresh) {
+                    km = 0;
+#pragma unroll
+                    for (int n = 0; n < 4; ++n)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t idx = (uint32_t)(qc + n * 8 + 2 * t + (e & 1)) * (uint32_t)S + k0 + g + (e >> 1) * 8;
+                            km |= (drop_keep(hkey, idx, drop.thresh) ? 1u : 0u) << (n * 4 + e);
+                        }
+                }
+                // dS^T = P^T (dropout'(dP^T) - delta) / 8 goes into dpt; then P^T is dropped in place for dV
 #pragma unroll
                 for (int n = 0; n < 4; ++n) {
                     const float2 ee = *reinterpret_cast<const float2*>(s_del + qc + n * 8 + 2 * t);
-                    st[n][0] *= (dpt[n][0] - ee.x) * 0.125f; st[n][1] *= (dpt[n][1] - ee.y) * 0.125f;
-                    st[n][2] *= (dpt[n][2] - ee.x) * 0.125f; st[n][3] *= (dpt[n][3] - ee.y) * 0.125f;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool kp = (km >> (n * 4 + e)) & 1u;
+                        const float dpe = drop.thresh ? (kp ? dpt[n][e] * drop.scale : 0.f) : dpt[n][e];
+                        dpt[n][e] = st[n][e] * (dpe - ((e & 1) ? ee.y : ee.x)) * 0.125f;
+                        if (drop.thresh) st[n][e] = kp ? st[n][e] * drop.scale : 0.f;
+                    }
                 }
-                mma_kn_t<2>(dk, st, sQ, qc, lane);        // dK += dS^T Q
+                mma_kn_t<2>(dv, st, sdO, qc, lane);       // dV += dropout(P)^T dO
+                mma_kn_t<2>(dk, dpt, sQ, qc, lane);       // dK += dS^T Q
             }
             store_c_bf16(dqkv, QKV_LD, base + k0, HID + h * HD, lane, dk, S, k0);
             store_c_bf16(dqkv, QKV_LD, base + k0, 2 * HID + h * HD, lane, dv, S, k0);
@@ -629,7 +667,16 @@ using namespace uc2;
 
 extern "C" UC2_API int uc2_attention_fwd(const void* qkv, const long long* attn_mask, void* ctx, float* lse, int B,
                                          int S, void* stream) {
+    return uc2_attention_fwd_dropout(qkv, attn_mask, ctx, lse, B, S, 0u, 0u, 1.f, stream);
+}
+
+extern "C" UC2_API int uc2_attention_fwd_dropout(const void* qkv, const long long* attn_mask, void* ctx, float* lse,
+                                                 int B, int S, unsigned int drop_key, unsigned int drop_thresh,
+                                                 float drop_scale, void* stream) {
     if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(drop_thresh < 65536u, UC2_ERR_ARG, "attention_fwd: drop_thresh must be < 65536");
+    UC2_REQUIRE(drop_thresh == 0 || S <= 256, UC2_ERR_UNSUPPORTED, "attention dropout is implemented for S <= 256 (S=%d)", S);
+    const DropCfg drop = {drop_key, drop_thresh, drop_scale};
     UC2_REQUIRE(qkv && attn_mask && ctx && lse, UC2_ERR_ARG, "attention_fwd: null pointer");
     UC2_REQUIRE(aligned16(qkv) && aligned16(ctx), UC2_ERR_ARG, "attention_fwd: qkv/ctx must be 16-byte aligned");
     int S_pad;
@@ -640,7 +687,7 @@ extern "C" UC2_API int uc2_attention_fwd(const void* qkv, const long long* attn_
         const int smem_bh = 3 * SP * 128 + SP * 4;
         if (int rc = set_smem(attention_fwd_bh_kernel, smem_bh)) return rc;
         attention_fwd_bh_kernel<<<dim3(NH, B), bh_warps(S) * 32, smem_bh, (cudaStream_t)stream>>>(
-            (const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, SP);
+            (const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, SP, drop);
         return check_last("attention_fwd_bh_kernel");
     }
     const int smem = TILE * 128 + 2 * S_pad * 128 + S_pad * 4;
@@ -653,7 +700,17 @@ extern "C" UC2_API int uc2_attention_fwd(const void* qkv, const long long* attn_
 extern "C" UC2_API int uc2_attention_bwd(const void* qkv, const long long* attn_mask, const void* ctx,
                                          const void* dctx, const float* lse, float* delta_ws, void* dqkv, int B,
                                          int S, void* stream) {
+    return uc2_attention_bwd_dropout(qkv, attn_mask, ctx, dctx, lse, delta_ws, dqkv, B, S, 0u, 0u, 1.f, stream);
+}
+
+extern "C" UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long long* attn_mask, const void* ctx,
+                                                 const void* dctx, const float* lse, float* delta_ws, void* dqkv,
+                                                 int B, int S, unsigned int drop_key, unsigned int drop_thresh,
+                                                 float drop_scale, void* stream) {
     if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(drop_thresh < 65536u, UC2_ERR_ARG, "attention_bwd: drop_thresh must be < 65536");
+    UC2_REQUIRE(drop_thresh == 0 || S <= 256, UC2_ERR_UNSUPPORTED, "attention dropout is implemented for S <= 256 (S=%d)", S);
+    const DropCfg drop = {drop_key, drop_thresh, drop_scale};
     UC2_REQUIRE(qkv && attn_mask && ctx && dctx && lse && delta_ws && dqkv, UC2_ERR_ARG, "attention_bwd: null pointer");
     UC2_REQUIRE(aligned16(qkv) && aligned16(ctx) && aligned16(dctx) && aligned16(dqkv), UC2_ERR_ARG,
                 "attention_bwd: tensors must be 16-byte aligned");
@@ -672,7 +729,7 @@ extern "C" UC2_API int uc2_attention_bwd(const void* qkv, const long long* attn_
         const int items = B * NH;
         const int grid = items < num_sms() ? items : num_sms();
         attention_bwd_bh_kernel<<<grid, bh_warps(S) * 32, smem_bh, s>>>((const bf16*)qkv, attn_mask, (const bf16*)dctx,
-                                                                       lse, delta_ws, (bf16*)dqkv, B, S, SP, nbuf);
+                                                                       lse, delta_ws, (bf16*)dqkv, B, S, SP, nbuf, drop);
         return check_last("attention_bwd_bh_kernel");
     }
     const int smem_dq = 2 * TILE * 128 + 2 * S_pad * 128 + S_pad * 4;

@@ -97,6 +97,26 @@ __device__ __forceinline__ void store8_f32(float* p, const float* f) {
     *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
+// Counter-based dropout (host mirror and rationale: uc2_b200/dropout.py).  keep <=> high 16 bits of the mixed
+// (element index ^ site key) are >= thresh = round(p * 65536); forward and backward regenerate the same mask.
+struct DropCfg {
+    uint32_t key;
+    uint32_t thresh;     // 0: dropout off
+    float scale;         // 1 / (1 - p)
+};
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ bool drop_keep(uint32_t key, uint32_t idx, uint32_t thresh) {
+    return (lowbias32(idx ^ key) >> 16) >= thresh;
+}
+__host__ __device__ __forceinline__ uint32_t drop_head_key(uint32_t key, uint32_t bh) {
+    return lowbias32(key ^ (bh * 0x9E3779B9u + 0x7F4A7C15u));
+}
+
 // erf-form GELU (model/layer.py:31-37) and its derivative.
 // 0.5 erfc(|x|/sqrt2) through Abramowitz-Stegun 7.1.25: erfc(z) = t (a1 + t (a2 + t a3)) exp(-z^2),
 // t = 1 / (1 + p z), z >= 0, |error| <= 2.5e-5 on erf.  The results are rounded to bf16 (half an ulp is 2e-3

@@ -58,6 +58,7 @@ struct GemmParams {
     float* out_f32; long long ld_f32;
     int accumulate;
     int vec_ok;   // leading dimensions / pointers allow 32-byte row-slice access -> vector epilogue
+    DropCfg drop; // dropout on (acc + bias) before the residual add (BertSelfOutput / BertOutput, layer.py:113,154)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float aux) {
@@ -82,26 +83,28 @@ __device__ __forceinline__ void store_bf16_row16(bf16* dst, const float* v) {
 //   5 FFN1/QKV dgrad : + bf16 residual                                   -> bf16
 //   6 wgrad          : fp32 atomic accumulate
 //   7 O-proj dgrad   : plain                                             -> bf16
+//   8 O-proj / FFN2  : dropout(+ bias) + fp32 residual (training)        -> fp32
 template <int MODE>
 struct Epi {
     static __device__ __forceinline__ bool bias(const GemmParams& p) {
-        return MODE == 0 ? p.bias != nullptr : (MODE == 1 || MODE == 3 || MODE == 4);
+        return MODE == 0 ? p.bias != nullptr : (MODE == 1 || MODE == 3 || MODE == 4 || MODE == 8);
     }
     static __device__ __forceinline__ bool out_pre(const GemmParams& p) { return MODE == 0 ? p.out_pre != nullptr : MODE == 1; }
     static __device__ __forceinline__ int act(const GemmParams& p) {
         return MODE == 0 ? p.act : (MODE == 1 ? UC2_ACT_GELU : (MODE == 2 ? UC2_ACT_DGELU : UC2_ACT_NONE));
     }
     static __device__ __forceinline__ bool residual(const GemmParams& p) {
-        return MODE == 0 ? p.residual != nullptr : (MODE == 3 || MODE == 5);
+        return MODE == 0 ? p.residual != nullptr : (MODE == 3 || MODE == 5 || MODE == 8);
     }
     static __device__ __forceinline__ bool out_bf16(const GemmParams& p) {
         return MODE == 0 ? p.out_bf16 != nullptr : (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 7);
     }
     static __device__ __forceinline__ bool out_f32(const GemmParams& p) {
-        return MODE == 0 ? p.out_f32 != nullptr : (MODE == 3 || MODE == 6);
+        return MODE == 0 ? p.out_f32 != nullptr : (MODE == 3 || MODE == 6 || MODE == 8);
     }
     static __device__ __forceinline__ bool accumulate(const GemmParams& p) { return MODE == 0 ? p.accumulate != 0 : MODE == 6; }
-    static constexpr int ex_kind = (MODE == 2 || MODE == 5) ? 1 : (MODE == 3 ? 2 : 0);   // meaningful for MODE != 0
+    static __device__ __forceinline__ bool dropout(const GemmParams& p) { return MODE == 0 ? p.drop.thresh != 0 : MODE == 8; }
+    static constexpr int ex_kind = (MODE == 2 || MODE == 5) ? 1 : ((MODE == 3 || MODE == 8) ? 2 : 0);   // for MODE != 0
 };
 
 __device__ __noinline__ void epilogue_scalar_row(const GemmParams& p, const float* acc, long long grow, int col0) {
@@ -116,6 +119,9 @@ __device__ __noinline__ void epilogue_scalar_row(const GemmParams& p, const floa
             const float a = p.act == UC2_ACT_DGELU ? __bfloat162float(p.aux[grow * p.ld_aux + gc]) : 0.f;
             x = apply_act(x, p.act, a);
         }
+        if (p.drop.thresh != 0)
+            x = drop_keep(p.drop.key, static_cast<uint32_t>(grow) * static_cast<uint32_t>(p.N) + gc, p.drop.thresh)
+                    ? x * p.drop.scale : 0.f;
         if (p.residual)
             x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[grow * p.ld_res + gc]
                            : __bfloat162float(p.residual[grow * p.ld_res + gc]);
@@ -221,6 +227,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                                 v[2 * j + 1] *= gelu_erf_grad(u.y);
                             }
                         }
+                    }
+                    if (F::dropout(p)) {
+                        const uint32_t i0 = static_cast<uint32_t>(grow) * static_cast<uint32_t>(p.N) + col0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = drop_keep(p.drop.key, i0 + j, p.drop.thresh) ? v[j] * p.drop.scale : 0.f;
                     }
                     if (EX == 2) {
 #pragma unroll
@@ -650,6 +662,8 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
     p.out_pre = static_cast<bf16*>(a.out_pre); p.ld_pre = a.ld_pre;
     p.out_f32 = a.out_f32; p.ld_f32 = a.ld_f32;
     p.accumulate = a.accumulate;
+    p.drop.key = a.drop_key; p.drop.thresh = a.drop_thresh; p.drop.scale = a.drop_scale;
+    UC2_REQUIRE(a.drop_thresh < 65536u, UC2_ERR_ARG, "uc2_gemm_bf16: drop_thresh must be < 65536");
     // 256-bit row slices: 32-byte aligned bases, pitches that keep every row 32-byte aligned
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     p.vec_ok = (!a.residual || (a.ld_res % (a.residual_f32 ? 8 : 16) == 0 && al32(a.residual))) &&
@@ -664,6 +678,11 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
         const bool bf = a.out_bf16 && !a.out_f32, f32o = a.out_f32 && !a.out_bf16;
         const bool kk = !a.a_mn && !a.b_mn, kn = !a.a_mn && a.b_mn, nn = a.a_mn && a.b_mn;
         const bool res32 = a.residual && a.residual_f32, resb = a.residual && !a.residual_f32;
+        if (a.drop_thresh != 0) {
+            if (kk && a.bias && !a.out_pre && a.act == UC2_ACT_NONE && res32 && f32o && !a.accumulate)
+                return launch<256, false, false, 2, 8>(a, p, s);
+            return dispatch_major<256, 2>(a, p, s);
+        }
         if (kk && a.bias && a.out_pre && a.act == UC2_ACT_GELU && !a.residual && bf)
             return launch<256, false, false, 2, 1>(a, p, s);
         if (kn && !a.bias && !a.out_pre && a.act == UC2_ACT_DGELU && !a.residual && bf)

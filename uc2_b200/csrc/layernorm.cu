@@ -75,7 +75,7 @@ template <bool F32>
 __global__ void __launch_bounds__(LN_WARPS * 32, 1)
 layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ gamma,
                      float eps, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                     float* __restrict__ dbias, long long rows) {
+                     float* __restrict__ dbias, long long rows, bf16* __restrict__ dxm, DropCfg drop) {
     constexpr int XB = F32 ? HID * 4 : HID * 2;       // bytes of one x row
     constexpr int SLOT = XB + HID * 2;                // x row + dy row
     extern __shared__ __align__(128) uint8_t ln_smem[];
@@ -140,12 +140,21 @@ layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, co
         s1 = warp_sum(s1) * (1.0f / HID);
         s2 = warp_sum(s2) * (1.0f / HID);
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            d[i] = rstd * (d[i] - s1 - v[i] * s2);
-            ax[i] += d[i];
-        }
+        for (int i = 0; i < VPL; ++i) d[i] = rstd * (d[i] - s1 - v[i] * s2);
 #pragma unroll
         for (int i = 0; i < 3; ++i) store8_bf16(dx + row * HID + col_of(lane, i), d + 8 * i);
+        if (dxm) {
+            // x was dropout(dense) + residual: the dense branch (its wgrad / dgrad / bias gradient) sees the masked,
+            // rescaled gradient, the residual branch the plain one written above
+            const uint32_t i0 = static_cast<uint32_t>(row) * HID;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i)
+                d[i] = drop_keep(drop.key, i0 + col_of(lane, i >> 3) + (i & 7), drop.thresh) ? d[i] * drop.scale : 0.f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) store8_bf16(dxm + row * HID + col_of(lane, i), d + 8 * i);
+        }
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) ax[i] += d[i];
     }
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -218,7 +227,18 @@ extern "C" UC2_API int uc2_layernorm_fwd(const void* x, int x_is_f32, const floa
 extern "C" UC2_API int uc2_layernorm_bwd(const void* x, int x_is_f32, const void* dy, const float* gamma, float eps,
                                          void* dx, float* dgamma, float* dbeta, float* dbias, long long rows,
                                          void* stream) {
+    return uc2_layernorm_bwd_dropout(x, x_is_f32, dy, gamma, eps, dx, dgamma, dbeta, dbias, rows, nullptr, 0u, 0u, 1.f,
+                                     stream);
+}
+
+extern "C" UC2_API int uc2_layernorm_bwd_dropout(const void* x, int x_is_f32, const void* dy, const float* gamma,
+                                                 float eps, void* dx, float* dgamma, float* dbeta, float* dbias,
+                                                 long long rows, void* dx_masked, unsigned int drop_key,
+                                                 unsigned int drop_thresh, float drop_scale, void* stream) {
     if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE((dx_masked != nullptr) == (drop_thresh != 0) && drop_thresh < 65536u && aligned16(dx_masked), UC2_ERR_ARG,
+                "layernorm_bwd: dx_masked goes with drop_thresh in (0, 65536)");
+    const DropCfg drop = {drop_key, drop_thresh, drop_scale};
     UC2_REQUIRE(x && dy && gamma && dx && dgamma && dbeta && rows > 0, UC2_ERR_ARG, "layernorm_bwd: bad args");
     UC2_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma), UC2_ERR_ARG,
                 "layernorm_bwd: pointers must be 16-byte aligned");
@@ -229,11 +249,11 @@ extern "C" UC2_API int uc2_layernorm_bwd(const void* x, int x_is_f32, const void
     if (x_is_f32) {
         UC2_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         layernorm_bwd_kernel<true><<<(unsigned)blocks, LN_WARPS * 32, smem, (cudaStream_t)stream>>>(
-            x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows);
+            x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows, (bf16*)dx_masked, drop);
     } else {
         UC2_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         layernorm_bwd_kernel<false><<<(unsigned)blocks, LN_WARPS * 32, smem, (cudaStream_t)stream>>>(
-            x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows);
+            x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows, (bf16*)dx_masked, drop);
     }
     return check_last("layernorm_bwd_kernel");
 }
