@@ -305,6 +305,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="itm", choices=["itm", "pretrain", "retrieval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="hidden / attention dropout of the training workloads (config/uc2-base.json: 0.1)")
     ap.add_argument("--layers", type=int, default=12, help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -318,7 +320,7 @@ def main():
             "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
             "config": {"workload": wl_name, "model": "uc2-base 12L/768H vocab 250002 random init",
-                       "per_gpu_batch": per_gpu, "seq_len": TXT + NBB, "dropout": 0.0,
+                       "per_gpu_batch": per_gpu, "seq_len": TXT + NBB, "dropout": args.dropout,
                        "l2": "working set (1.1 GB fp32 params + >5 GB activations per step) far exceeds the 126 MB L2"}}
 
     if args.impl == "reference":
@@ -371,7 +373,7 @@ def main():
     model.load_state_dict(sd, strict=False)
     del sd
     model.to(dev).train()
-    set_dropout(model, 0.0)
+    set_dropout(model, args.dropout)
     arena = model._arena()
     D.broadcast_arena(arena)
     groups = [{"params": [p for n, p in model.named_parameters()], "weight_decay": 0.0}]

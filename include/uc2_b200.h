@@ -122,6 +122,10 @@ typedef struct {
     const float* fin_ln_w; const float* fin_ln_b;
     float eps;
     int vocab, max_pos;
+    /* nn.Dropout on the text / image embeddings (model/model.py:334, 363), applied before the pack: element
+     * (b, source row, col) is kept iff (lowbias32(((b * (T + R) + src) * 768 + col) ^ drop_key) >> 16) >= drop_thresh,
+     * src = t for text, T + r for regions; drop_thresh = 0 disables it. */
+    unsigned int drop_key; unsigned int drop_thresh; float drop_scale;
 } uc2_embed_args;
 
 typedef struct {                 /* fp32 gradient accumulators (+=), same shapes as the parameters */
@@ -223,7 +227,16 @@ typedef struct {
     void* g;      /* [M,3072] gelu(u) */
     void* z2;     /* [M,768]  fp32: FFN2 + bias + residual */
     void* out;    /* [M,768]  layer output */
+    /* dropout site keys of this layer (attention probabilities, attention output, FFN output); used when the
+     * uc2_dropout argument of uc2_encoder_fwd / _bwd enables the site.  Living here, they stay attached to the
+     * layer when backward runs over sub-ranges of layers. */
+    unsigned int key_attn, key_out1, key_out2;
 } uc2_layer_acts;
+
+typedef struct {
+    unsigned int attn_thresh; float attn_scale;       /* attention_probs_dropout_prob (model/layer.py:94) */
+    unsigned int hidden_thresh; float hidden_scale;   /* hidden_dropout_prob (model/layer.py:113, 154) */
+} uc2_dropout;
 
 /* x_in: bf16 [M,768] embedding output; x_in_f32: the same rows in fp32 (start of the residual stream).
  * workspace: uc2_encoder_fwd_workspace_bytes(B,S) bytes, 256-byte aligned (rotating fp32 residual buffers). */
@@ -231,11 +244,20 @@ UC2_API size_t uc2_encoder_fwd_workspace_bytes(int B, int S);
 UC2_API int uc2_encoder_fwd(const void* x_in, const float* x_in_f32, const long long* attn_mask, int B, int S,
                             int n_layers, const uc2_layer_weights* w, const uc2_layer_acts* acts, int save_for_bwd,
                             void* workspace, size_t workspace_bytes, void* stream);
+/* Training forms: `drop` (may be NULL = no dropout) switches the three per-layer dropout sites on. */
+UC2_API int uc2_encoder_fwd_dropout(const void* x_in, const float* x_in_f32, const long long* attn_mask, int B, int S,
+                                    int n_layers, const uc2_layer_weights* w, const uc2_layer_acts* acts,
+                                    int save_for_bwd, const uc2_dropout* drop, void* workspace, size_t workspace_bytes,
+                                    void* stream);
 UC2_API size_t uc2_encoder_bwd_workspace_bytes(int B, int S);
 /* dout: bf16 [M,768] gradient of the last layer's output; dx_in: bf16 [M,768] gradient of x_in (written). */
 UC2_API int uc2_encoder_bwd(const void* x_in, const long long* attn_mask, int B, int S, int n_layers,
                             const uc2_layer_weights* w, const uc2_layer_acts* acts, const uc2_layer_grads* grads,
                             const void* dout, void* dx_in, void* workspace, size_t workspace_bytes, void* stream);
+UC2_API int uc2_encoder_bwd_dropout(const void* x_in, const long long* attn_mask, int B, int S, int n_layers,
+                                    const uc2_layer_weights* w, const uc2_layer_acts* acts, const uc2_layer_grads* grads,
+                                    const void* dout, void* dx_in, const uc2_dropout* drop, void* workspace,
+                                    size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Heads and losses (warp-level kernels).

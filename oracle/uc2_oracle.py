@@ -148,8 +148,9 @@ def pack(txt_emb, img_emb, gi):
     return torch.gather(cat, 1, gi.unsqueeze(-1).expand(-1, -1, cat.size(-1)))
 
 
-def self_attention(sd, pre, x, ext_mask, n_heads=12):
-    """model/layer.py:75-101."""
+def self_attention(sd, pre, x, ext_mask, n_heads=12, drop_attn=None):
+    """model/layer.py:75-101.  drop_attn: optional [B, heads, S, S] multiplier (0 or 1/(1-p)) standing in for
+    nn.Dropout on the attention probabilities (layer.py:94)."""
     B, S, Hd = x.shape
     d = Hd // n_heads
 
@@ -159,20 +160,27 @@ def self_attention(sd, pre, x, ext_mask, n_heads=12):
     q, k, v = proj("query"), proj("key"), proj("value")
     s = q @ k.transpose(-1, -2) / math.sqrt(d) + ext_mask
     pr = torch.softmax(s, -1)
+    if drop_attn is not None:
+        pr = pr * drop_attn
     return (pr @ v).permute(0, 2, 1, 3).reshape(B, S, Hd)
 
 
-def bert_layer(sd, pre, x, ext_mask, n_heads=12):
+def bert_layer(sd, pre, x, ext_mask, n_heads=12, drop=None):
     """model/layer.py:159-170 (A6->A7->A8->A9); LayerNorm eps is 1e-12 in both families
-    (layer.py:108,149)."""
-    ctx = self_attention(sd, pre, x, ext_mask, n_heads)
-    a = layer_norm(F.linear(ctx, sd[pre + "attention.output.dense.weight"],
-                            sd[pre + "attention.output.dense.bias"]) + x,
-                   sd[pre + "attention.output.LayerNorm.weight"],
+    (layer.py:108,149).  drop: optional (attn [B,h,S,S], out1 [B,S,H], out2 [B,S,H]) multipliers for the three
+    nn.Dropout sites (layer.py:94, 113, 154); None = evaluation / p = 0."""
+    d_attn, d_out1, d_out2 = drop if drop is not None else (None, None, None)
+    ctx = self_attention(sd, pre, x, ext_mask, n_heads, d_attn)
+    o1 = F.linear(ctx, sd[pre + "attention.output.dense.weight"], sd[pre + "attention.output.dense.bias"])
+    if d_out1 is not None:
+        o1 = o1 * d_out1
+    a = layer_norm(o1 + x, sd[pre + "attention.output.LayerNorm.weight"],
                    sd[pre + "attention.output.LayerNorm.bias"], 1e-12)
     i = gelu_erf(F.linear(a, sd[pre + "intermediate.dense.weight"], sd[pre + "intermediate.dense.bias"]))
-    return layer_norm(F.linear(i, sd[pre + "output.dense.weight"], sd[pre + "output.dense.bias"]) + a,
-                      sd[pre + "output.LayerNorm.weight"], sd[pre + "output.LayerNorm.bias"], 1e-12)
+    o2 = F.linear(i, sd[pre + "output.dense.weight"], sd[pre + "output.dense.bias"])
+    if d_out2 is not None:
+        o2 = o2 * d_out2
+    return layer_norm(o2 + a, sd[pre + "output.LayerNorm.weight"], sd[pre + "output.LayerNorm.bias"], 1e-12)
 
 
 def n_layers(sd, fam):
@@ -183,8 +191,10 @@ def n_layers(sd, fam):
 
 
 def encoder(sd, fam, input_ids, position_ids, img_feat, img_pos_feat, attention_mask,
-            gather_index=None, img_masks=None, all_layers=False):
-    """model/model.py:427-458 == 1109-1140."""
+            gather_index=None, img_masks=None, all_layers=False, drop=None):
+    """model/model.py:427-458 == 1109-1140.  drop: optional dict of dropout multipliers (training mode with the
+    masks given explicitly): "emb" [B, T+R, H] on cat(text, image) embeddings before the pack (model.py:334, 363),
+    "layers": list of (attn, out1, out2) per layer."""
     am = torch.as_tensor(attention_mask)
     ext = (1.0 - am[:, None, None, :].to(torch.float32)) * -10000.0
     if input_ids is None:
@@ -192,11 +202,16 @@ def encoder(sd, fam, input_ids, position_ids, img_feat, img_pos_feat, attention_
     elif img_feat is None:
         x = text_embeddings(sd, fam, input_ids, position_ids)
     else:
-        x = pack(text_embeddings(sd, fam, input_ids, position_ids),
-                 image_embeddings(sd, fam, img_feat, img_pos_feat, img_masks), gather_index)
+        te = text_embeddings(sd, fam, input_ids, position_ids)
+        ie = image_embeddings(sd, fam, img_feat, img_pos_feat, img_masks)
+        if drop is not None and drop.get("emb") is not None:
+            T = te.size(1)
+            te, ie = te * drop["emb"][:, :T], ie * drop["emb"][:, T:]
+        x = pack(te, ie, gather_index)
     outs = [x]
     for l in range(n_layers(sd, fam)):
-        x = bert_layer(sd, fam.enc + f"encoder.layer.{l}.", x, ext)
+        x = bert_layer(sd, fam.enc + f"encoder.layer.{l}.", x, ext,
+                       drop=drop["layers"][l] if drop is not None else None)
         outs.append(x)
     return outs if all_layers else x
 
@@ -352,7 +367,7 @@ def pretraining_loss(out, task, itm_ot_lambda=0.1, ot_pos_only=False):
     return out.mean()
 
 
-def forward_retrieval(sd, fam, batch, compute_loss=True, margin=0.2):
+def forward_retrieval(sd, fam, batch, compute_loss=True, margin=0.2, drop=None):
     """model/itm.py:28-55."""
     pos = None if fam.name == "vlxlmr" else batch.get("position_ids")
     h = encoder(sd, fam, batch["input_ids"], pos, batch["img_feat"], batch["img_pos_feat"],

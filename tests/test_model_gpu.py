@@ -279,3 +279,76 @@ def test_retrieval_scoring_and_ranking(golden):
     assert torch.equal(s0, sm[0::2]) and torch.equal(s1, sm[1::2])
     log = retrieval.itm_eval(sm.float(), txt_ids, arena.img_ids, txt2img, img2txts)
     assert set(log) == {"txt_r1", "txt_r5", "txt_r10", "txt_r_mean", "img_r1", "img_r5", "img_r10", "img_r_mean", "r_mean"}
+
+
+def _dropout_multipliers(seed, counter, B, T, R, S, L, p_h, p_a):
+    """The masks the kernels regenerate (uc2_b200/dropout.py), as float multipliers for the oracle."""
+    from uc2_b200 import dropout as DO
+    th, sh, ta, sa = DO.thresh_of(p_h), DO.scale_of(p_h), DO.thresh_of(p_a), DO.scale_of(p_a)
+    f = lambda key, n, t, s: torch.from_numpy(DO.keep_mask_np(key, n, t).astype(np.float32) * np.float32(s))
+    emb = f(DO.site_key(seed, counter, 255, DO.SITE_EMB), B * (T + R) * 768, th, sh).view(B, T + R, 768)
+    layers = []
+    for l in range(L):
+        ka = DO.site_key(seed, counter, l, DO.SITE_ATTN)
+        attn = torch.stack([f(DO.head_key(ka, bh), S * S, ta, sa).view(S, S) for bh in range(B * 12)]).view(B, 12, S, S)
+        o1 = f(DO.site_key(seed, counter, l, DO.SITE_OUT1), B * S * 768, th, sh).view(B, S, 768)
+        o2 = f(DO.site_key(seed, counter, l, DO.SITE_OUT2), B * S * 768, th, sh).view(B, S, 768)
+        layers.append((attn, o1, o2))
+    return {"emb": emb, "layers": layers}
+
+
+@pytest.mark.parametrize("p_h,p_a", [(0.1, 0.1), (0.25, 0.0), (0.0, 0.3)])
+def test_dropout_training_mode_matches_oracle_with_same_masks(p_h, p_a):
+    """Training mode with dropout: the five nn.Dropout sites of the reference (model.py:334, 363; layer.py:94, 113,
+    154) as counter-based masks.  The oracle runs the same network with exactly those masks plugged in; outputs and
+    every parameter gradient of the encoder must agree, which pins forward/backward mask consistency at all sites."""
+    from oracle import uc2_oracle as O
+    cfg = cases.config(2)
+    m, sd = build("pretrain", cfg)
+    m.train()
+    for n, mod in m.named_modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = p_a if n.endswith("attention.self.dropout") else p_h
+    torch.manual_seed(321)
+    b = cases.batch_mrfr(seed=5)
+    db = dev(b)
+    enc = m.roberta
+    h = enc(db["input_ids"], None, db["img_feat"], db["img_pos_feat"], db["attn_masks"], db["gather_index"],
+            img_masks=db["img_masks"], output_all_encoded_layers=False)
+    counter = m._uc2_drop_counter
+    B, S, _ = h.shape
+    T, R = b["input_ids"].size(1), b["img_feat"].size(1)
+    wgt = torch.from_numpy(cases.synth.det_normal((B, S, 768), 99).astype(np.float32))
+    (h.float() * wgt.cuda()).sum().div(B).backward()
+    drop = _dropout_multipliers(321, counter, B, T, R, S, 2, p_h, p_a)
+    kept = float((drop["layers"][0][1] != 0).float().mean())
+    assert abs(kept - (1 - p_h)) < 5e-3
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    href = O.encoder(sdg, O.Family("vlxlmr"), b["input_ids"], None, b["img_feat"], b["img_pos_feat"], b["attn_masks"],
+                     b["gather_index"], b["img_masks"], drop=drop)
+    (href * wgt).sum().div(B).backward()
+    close(h.float().detach().cpu().numpy(), href.detach().numpy(), what="hidden states with dropout")
+    top = max(float(v.grad.norm()) for v in sdg.values() if v.grad is not None)
+    checked = 0
+    for n_, p_ in m.named_parameters():
+        gr = sdg[n_].grad
+        if gr is None or float(gr.norm()) < 1e-4 * top:
+            continue
+        rel = float((p_.grad.detach().cpu() - gr).norm() / gr.norm())
+        assert rel <= 3e-2, f"{n_}: relative gradient error {rel:.4f} with dropout"
+        checked += 1
+    assert checked > 30
+    # evaluation mode: dropout is off and two calls agree bit for bit; training mode draws fresh masks per call
+    m.eval()
+    with torch.no_grad():
+        e1 = enc(db["input_ids"], None, db["img_feat"], db["img_pos_feat"], db["attn_masks"], db["gather_index"],
+                 output_all_encoded_layers=False)
+        e2 = enc(db["input_ids"], None, db["img_feat"], db["img_pos_feat"], db["attn_masks"], db["gather_index"],
+                 output_all_encoded_layers=False)
+        assert torch.equal(e1, e2)
+        m.train()
+        t1 = enc(db["input_ids"], None, db["img_feat"], db["img_pos_feat"], db["attn_masks"], db["gather_index"],
+                 output_all_encoded_layers=False)
+        t2 = enc(db["input_ids"], None, db["img_feat"], db["img_pos_feat"], db["attn_masks"], db["gather_index"],
+                 output_all_encoded_layers=False)
+        assert not torch.equal(t1, t2)

@@ -32,7 +32,8 @@ class EmbedArgs(C.Structure):
                 ("word_emb", P), ("pos_emb", P), ("type_emb", P), ("ln_w", P), ("ln_b", P),
                 ("y_img", P), ("img_pos_feat", P), ("img_ln_w", P), ("img_ln_b", P),
                 ("pos_w", P), ("pos_b", P), ("pos_ln_w", P), ("pos_ln_b", P),
-                ("fin_ln_w", P), ("fin_ln_b", P), ("eps", F), ("vocab", I), ("max_pos", I)]
+                ("fin_ln_w", P), ("fin_ln_b", P), ("eps", F), ("vocab", I), ("max_pos", I),
+                ("drop_key", C.c_uint), ("drop_thresh", C.c_uint), ("drop_scale", F)]
 
 
 class EmbedGrads(C.Structure):
@@ -54,7 +55,11 @@ class LayerGrads(C.Structure):
 
 
 class LayerActs(C.Structure):
-    _fields_ = [(n, P) for n in ACT_FIELDS]
+    _fields_ = [(n, P) for n in ACT_FIELDS] + [("key_attn", C.c_uint), ("key_out1", C.c_uint), ("key_out2", C.c_uint)]
+
+
+class Dropout(C.Structure):
+    _fields_ = [("attn_thresh", C.c_uint), ("attn_scale", F), ("hidden_thresh", C.c_uint), ("hidden_scale", F)]
 
 
 class OptChunk(C.Structure):
@@ -75,6 +80,13 @@ _SIGS = {
     "uc2_vecmat_acc": [P, P, P, I, I, P],
     "uc2_layernorm_fwd": [P, I, P, P, F, P, P, LL, P],
     "uc2_layernorm_bwd": [P, I, P, P, F, P, P, P, P, LL, P],
+    "uc2_layernorm_bwd_dropout": [P, I, P, P, F, P, P, P, P, LL, P, C.c_uint, C.c_uint, F, P],
+    "uc2_attention_fwd_dropout": [P, P, P, P, I, I, C.c_uint, C.c_uint, F, P],
+    "uc2_attention_bwd_dropout": [P, P, P, P, P, P, P, I, I, C.c_uint, C.c_uint, F, P],
+    "uc2_encoder_fwd_dropout": [P, P, P, I, I, I, C.POINTER(LayerWeights), C.POINTER(LayerActs), I, C.POINTER(Dropout),
+                                P, SZ, P],
+    "uc2_encoder_bwd_dropout": [P, P, I, I, I, C.POINTER(LayerWeights), C.POINTER(LayerActs), C.POINTER(LayerGrads),
+                                P, P, C.POINTER(Dropout), P, SZ, P],
     "uc2_colsum_bf16": [P, LL, LL, I, P, P],
     "uc2_attention_fwd": [P, P, P, P, I, I, P],
     "uc2_attention_bwd": [P, P, P, P, P, P, P, I, I, P],

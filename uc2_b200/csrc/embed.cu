@@ -69,9 +69,22 @@ struct EmbedParams {
     const float* fin_ln_w; const float* fin_ln_b;    // img_embeddings.LayerNorm
     float eps;
     int vocab, max_pos;
+    DropCfg drop;                   // dropout on the embedding outputs (model.py:334, 363), indexed by SOURCE row
 };
 
 struct Src { int is_img; int idx; };   // idx: token column t or region r
+
+// Embedding dropout acts on the text / image embedding tensors BEFORE the gather_index pack, so the mask is a
+// function of the source row b * (T + R) + (t | T + r): packed pad columns that alias a real row share its mask.
+__device__ __forceinline__ void embed_dropout(const EmbedParams& p, int b, const Src& s, int lane, float* v) {
+    if (p.drop.thresh == 0) return;
+    const uint32_t src_row = (uint32_t)b * (uint32_t)(p.T + p.R) + (uint32_t)(s.is_img ? p.T + s.idx : s.idx);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const uint32_t idx = src_row * HID + col_of(lane, i >> 3) + (i & 7);
+        v[i] = drop_keep(p.drop.key, idx, p.drop.thresh) ? v[i] * p.drop.scale : 0.f;
+    }
+}
 
 __device__ __forceinline__ Src resolve(const EmbedParams& p, int b, int j) {
     Src s;
@@ -152,6 +165,7 @@ embed_pack_fwd_kernel(const EmbedParams p, bf16* __restrict__ out, float* __rest
         for (int i = 0; i < VPL; ++i) v[i] += q[i] + t1[i];
         ln_apply(v, p.fin_ln_w, p.fin_ln_b, lane, p.eps);
     }
+    embed_dropout(p, b, s, lane, v);
     store_row_bf16(out + row * HID, lane, v);
     if (out32) {
 #pragma unroll
@@ -230,6 +244,7 @@ embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const 
 #pragma unroll
         for (int i = 0; i < VPL; ++i) nz += fabsf(dy[i]);
         if (warp_sum(nz) == 0.f) continue;       // rows that received no gradient (pads) add nothing
+        embed_dropout(p, b, s, lane, dy);
         float x[VPL];
         if (!s.is_img) {
             const long long id = p.input_ids[(long long)b * p.T + s.idx];
@@ -364,6 +379,8 @@ int fill_params(EmbedParams& p, const uc2_embed_args& a) {
     p.y_img = a.y_img; p.pos_feat = a.img_pos_feat; p.img_ln_w = a.img_ln_w; p.img_ln_b = a.img_ln_b;
     p.pos_w = a.pos_w; p.pos_b = a.pos_b; p.pos_ln_w = a.pos_ln_w; p.pos_ln_b = a.pos_ln_b;
     p.fin_ln_w = a.fin_ln_w; p.fin_ln_b = a.fin_ln_b; p.eps = a.eps; p.vocab = a.vocab; p.max_pos = a.max_pos;
+    p.drop.key = a.drop_key; p.drop.thresh = a.drop_thresh; p.drop.scale = a.drop_scale;
+    UC2_REQUIRE(a.drop_thresh < 65536u, UC2_ERR_ARG, "embed_pack: drop_thresh must be < 65536");
     if (a.mode == 0) UC2_REQUIRE(a.gather_index, UC2_ERR_ARG, "embed: joint mode needs gather_index");
     if (a.mode != 2) UC2_REQUIRE(a.input_ids && a.word_emb && a.pos_emb && a.type_emb && a.ln_w && a.ln_b,
                                  UC2_ERR_ARG, "embed: text inputs missing");

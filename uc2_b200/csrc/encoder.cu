@@ -72,14 +72,25 @@ extern "C" UC2_API size_t uc2_encoder_fwd_workspace_bytes(int B, int S) {
 
 extern "C" UC2_API size_t uc2_encoder_bwd_workspace_bytes(int B, int S) {
     const size_t M = (size_t)B * S;
-    // 4 x [M,768] + [M,3072] + [M,2304] bf16, + delta fp32 [B,12,S]; each region 256-byte aligned
-    return 4 * al256(M * HID * 2) + al256(M * FF * 2) + al256(M * QKV * 2) + al256(M * 12 * 4);
+    // 6 x [M,768] (two of them only used with dropout) + [M,3072] + [M,2304] bf16, + delta fp32 [B,12,S];
+    // each region 256-byte aligned
+    return 6 * al256(M * HID * 2) + al256(M * FF * 2) + al256(M * QKV * 2) + al256(M * 12 * 4);
 }
 
 extern "C" UC2_API int uc2_encoder_fwd(const void* x_in, const float* x_in_f32, const long long* attn_mask, int B,
                                        int S, int n_layers, const uc2_layer_weights* w, const uc2_layer_acts* acts,
                                        int save_for_bwd, void* workspace, size_t workspace_bytes, void* stream) {
+    return uc2_encoder_fwd_dropout(x_in, x_in_f32, attn_mask, B, S, n_layers, w, acts, save_for_bwd, nullptr, workspace,
+                                   workspace_bytes, stream);
+}
+
+extern "C" UC2_API int uc2_encoder_fwd_dropout(const void* x_in, const float* x_in_f32, const long long* attn_mask,
+                                               int B, int S, int n_layers, const uc2_layer_weights* w,
+                                               const uc2_layer_acts* acts, int save_for_bwd, const uc2_dropout* drop,
+                                               void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = require_sm100()) return rc;
+    const uc2_dropout nodrop = {0u, 1.f, 0u, 1.f};
+    const uc2_dropout& D = drop ? *drop : nodrop;
     UC2_REQUIRE(x_in && x_in_f32 && attn_mask && w && acts && workspace && n_layers > 0 && B > 0 && S > 0, UC2_ERR_ARG,
                 "encoder_fwd: bad args");
     UC2_REQUIRE(workspace_bytes >= uc2_encoder_fwd_workspace_bytes(B, S), UC2_ERR_ARG, "encoder_fwd: workspace too small");
@@ -104,9 +115,12 @@ extern "C" UC2_API int uc2_encoder_fwd(const void* x_in, const float* x_in_f32, 
             g.out_bf16 = A.qkv; g.ld_out = QKV;
             if (int rc = run(s, g)) return rc;
         }
-        if (int rc = uc2_attention_fwd(A.qkv, attn_mask, A.ctx, A.lse, B, S, stream)) return rc;
-        {   // attention output projection + bias + residual -> fp32 LayerNorm input
+        if (int rc = uc2_attention_fwd_dropout(A.qkv, attn_mask, A.ctx, A.lse, B, S, A.key_attn, D.attn_thresh,
+                                               D.attn_scale, stream))
+            return rc;
+        {   // attention output projection + bias (+ dropout) + residual -> fp32 LayerNorm input
             G g = linear_fwd(A.ctx, W.w_o, W.b_o, M, HID, HID);
+            g.drop = DropCfg{A.key_out1, D.hidden_thresh, D.hidden_scale};
             g.residual = xr; g.ld_res = HID; g.res_f32 = true;
             g.out_f32 = static_cast<float*>(A.z1); g.ld_f32 = HID;
             if (int rc = run(s, g)) return rc;
@@ -118,8 +132,9 @@ extern "C" UC2_API int uc2_encoder_fwd(const void* x_in, const float* x_in_f32, 
             if (save_for_bwd) { g.out_pre = A.u; g.ld_pre = FF; }
             if (int rc = run(s, g)) return rc;
         }
-        {   // FFN2 + bias + residual
+        {   // FFN2 + bias (+ dropout) + residual
             G g = linear_fwd(A.g, W.w_ffn2, W.b_ffn2, M, HID, FF);
+            g.drop = DropCfg{A.key_out2, D.hidden_thresh, D.hidden_scale};
             g.residual = h1r; g.ld_res = HID; g.res_f32 = true;
             g.out_f32 = static_cast<float*>(A.z2); g.ld_f32 = HID;
             if (int rc = run(s, g)) return rc;
@@ -136,7 +151,19 @@ extern "C" UC2_API int uc2_encoder_bwd(const void* x_in, const long long* attn_m
                                        const uc2_layer_weights* w, const uc2_layer_acts* acts,
                                        const uc2_layer_grads* grads, const void* dout, void* dx_in, void* workspace,
                                        size_t workspace_bytes, void* stream) {
+    return uc2_encoder_bwd_dropout(x_in, attn_mask, B, S, n_layers, w, acts, grads, dout, dx_in, nullptr, workspace,
+                                   workspace_bytes, stream);
+}
+
+extern "C" UC2_API int uc2_encoder_bwd_dropout(const void* x_in, const long long* attn_mask, int B, int S, int n_layers,
+                                               const uc2_layer_weights* w, const uc2_layer_acts* acts,
+                                               const uc2_layer_grads* grads, const void* dout, void* dx_in,
+                                               const uc2_dropout* drop, void* workspace, size_t workspace_bytes,
+                                               void* stream) {
     if (int rc = require_sm100()) return rc;
+    const uc2_dropout nodrop = {0u, 1.f, 0u, 1.f};
+    const uc2_dropout& D = drop ? *drop : nodrop;
+    const bool hd = D.hidden_thresh != 0;
     UC2_REQUIRE(x_in && attn_mask && w && acts && grads && dout && dx_in && workspace && n_layers > 0, UC2_ERR_ARG,
                 "encoder_bwd: bad args");
     UC2_REQUIRE(workspace_bytes >= uc2_encoder_bwd_workspace_bytes(B, S), UC2_ERR_ARG,
@@ -145,8 +172,8 @@ extern "C" UC2_API int uc2_encoder_bwd(const void* x_in, const long long* attn_m
     cudaStream_t s = (cudaStream_t)stream;
     const int M = B * S;
     uint8_t* p = static_cast<uint8_t*>(workspace);
-    void* ws768[4];
-    for (int i = 0; i < 4; ++i) { ws768[i] = p; p += al256((size_t)M * HID * 2); }
+    void* ws768[6];
+    for (int i = 0; i < 6; ++i) { ws768[i] = p; p += al256((size_t)M * HID * 2); }
     void* du = p; p += al256((size_t)M * FF * 2);
     void* dqkv = p; p += al256((size_t)M * QKV * 2);
     float* delta = reinterpret_cast<float*>(p);
@@ -162,14 +189,18 @@ extern "C" UC2_API int uc2_encoder_bwd(const void* x_in, const long long* attn_m
         void* dz2 = ws768[flip];
         void* dh1 = ws768[2];                   // later reused for dctx
         void* dz1 = ws768[3];
+        // with hidden dropout the dense branches see the masked, rescaled gradients; the residual adds the plain ones
+        void* dz2m = hd ? ws768[4] : dz2;
+        void* dz1m = hd ? ws768[5] : dz1;
         void* d_next = l == 0 ? dx_in : dz2;    // dz2 is last read by the FFN1 dgrad, long before this is written
         UC2_REQUIRE(A.u, UC2_ERR_ARG, "encoder_bwd: layer %d has no saved pre-GELU activation", l);
         // output LayerNorm + FFN2
-        if (int rc = uc2_layernorm_bwd(A.z2, 1, d_cur, W.ln2_w, 1e-12f, dz2, Gr.ln2_w, Gr.ln2_b, Gr.b_ffn2, M, stream))
+        if (int rc = uc2_layernorm_bwd_dropout(A.z2, 1, d_cur, W.ln2_w, 1e-12f, dz2, Gr.ln2_w, Gr.ln2_b, Gr.b_ffn2, M,
+                                               hd ? dz2m : nullptr, A.key_out2, D.hidden_thresh, D.hidden_scale, stream))
             return rc;
-        if (int rc = run(s, linear_wgrad(dz2, A.g, M, HID, FF, Gr.w_ffn2))) return rc;
+        if (int rc = run(s, linear_wgrad(dz2m, A.g, M, HID, FF, Gr.w_ffn2))) return rc;
         {
-            G g = linear_dgrad(dz2, W.w_ffn2, M, HID, FF, du);
+            G g = linear_dgrad(dz2m, W.w_ffn2, M, HID, FF, du);
             g.aux = A.u; g.ld_aux = FF; g.act = UC2_ACT_DGELU;
             if (int rc = run(s, g)) return rc;
         }
@@ -182,13 +213,16 @@ extern "C" UC2_API int uc2_encoder_bwd(const void* x_in, const long long* attn_m
             if (int rc = run(s, g)) return rc;
         }
         // attention-output LayerNorm + projection
-        if (int rc = uc2_layernorm_bwd(A.z1, 1, dh1, W.ln1_w, 1e-12f, dz1, Gr.ln1_w, Gr.ln1_b, Gr.b_o, M, stream))
+        if (int rc = uc2_layernorm_bwd_dropout(A.z1, 1, dh1, W.ln1_w, 1e-12f, dz1, Gr.ln1_w, Gr.ln1_b, Gr.b_o, M,
+                                               hd ? dz1m : nullptr, A.key_out1, D.hidden_thresh, D.hidden_scale, stream))
             return rc;
-        if (int rc = run(s, linear_wgrad(dz1, A.ctx, M, HID, HID, Gr.w_o))) return rc;
+        if (int rc = run(s, linear_wgrad(dz1m, A.ctx, M, HID, HID, Gr.w_o))) return rc;
         void* dctx = dh1;
-        if (int rc = run(s, linear_dgrad(dz1, W.w_o, M, HID, HID, dctx))) return rc;
+        if (int rc = run(s, linear_dgrad(dz1m, W.w_o, M, HID, HID, dctx))) return rc;
         // attention + QKV projection
-        if (int rc = uc2_attention_bwd(A.qkv, attn_mask, A.ctx, dctx, A.lse, delta, dqkv, B, S, stream)) return rc;
+        if (int rc = uc2_attention_bwd_dropout(A.qkv, attn_mask, A.ctx, dctx, A.lse, delta, dqkv, B, S, A.key_attn,
+                                               D.attn_thresh, D.attn_scale, stream))
+            return rc;
         if (int rc = uc2_colsum_bf16(dqkv, QKV, M, QKV, Gr.b_qkv, stream)) return rc;
         if (int rc = run(s, linear_wgrad(dqkv, x_l, M, QKV, HID, Gr.w_qkv))) return rc;
         {

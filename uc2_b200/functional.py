@@ -7,6 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
+from . import dropout as DO
 from ._lib import call, ptr, stream
 
 BF16, F32 = torch.bfloat16, torch.float32
@@ -25,8 +26,10 @@ class EncoderState(object):
 
 
 def encoder_forward(enc, arena, input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index,
-                    img_masks, save, embed_only=False, keep_all=False):
-    """Runs K1-K10.  Returns (x0, [layer outputs], state)."""
+                    img_masks, save, embed_only=False, keep_all=False, dropout=None):
+    """Runs K1-K10.  Returns (x0, [layer outputs], state).
+    dropout: None, or (p_hidden, p_attn, seed, counter) -- the five nn.Dropout sites of the reference
+    (model.py:334, 363; layer.py:94, 113, 154) as counter-based masks regenerated in backward (dropout.py)."""
     cfg, fam = enc.config, enc.family
     pre = enc.prefix
     dev = attention_mask.device
@@ -44,6 +47,13 @@ def encoder_forward(enc, arena, input_ids, position_ids, img_feat, img_pos_feat,
     a.word_pad_id, a.pos_pad_id = fam.word_pad, fam.pos_pad
     a.eps = fam.emb_eps(cfg)
     a.vocab, a.max_pos = cfg.vocab_size, cfg.max_position_embeddings
+    a.drop_scale = 1.0
+    drop = None
+    if dropout is not None:
+        p_h, p_a, seed, counter = dropout
+        a.drop_key, a.drop_thresh = DO.site_key(seed, counter, 255, DO.SITE_EMB), DO.thresh_of(p_h)
+        a.drop_scale = DO.scale_of(p_h)
+        drop = _lib.Dropout(DO.thresh_of(p_a), DO.scale_of(p_a), DO.thresh_of(p_h), DO.scale_of(p_h))
     a.type_emb = arena.mp(pre + fam.type_emb)
     keep = []
     if has_txt:
@@ -115,12 +125,16 @@ def encoder_forward(enc, arena, input_ids, position_ids, img_feat, img_pos_feat,
         outs.append(b["out"])
         for f in _lib.ACT_FIELDS:
             setattr(acts[l], f, ptr(b[f]))
+        if dropout is not None:
+            acts[l].key_attn = DO.site_key(seed, counter, l, DO.SITE_ATTN)
+            acts[l].key_out1 = DO.site_key(seed, counter, l, DO.SITE_OUT1)
+            acts[l].key_out2 = DO.site_key(seed, counter, l, DO.SITE_OUT2)
     fws_bytes = int(_lib.lib().uc2_encoder_fwd_workspace_bytes(B, S))
     fws = torch.empty(fws_bytes, dtype=torch.uint8, device=dev)
-    call("uc2_encoder_fwd", x0.data_ptr(), x0_f32.data_ptr(), am.data_ptr(), B, S, L, W, acts, int(save),
-         fws.data_ptr(), fws_bytes, stream())
+    call("uc2_encoder_fwd_dropout", x0.data_ptr(), x0_f32.data_ptr(), am.data_ptr(), B, S, L, W, acts, int(save),
+         C.byref(drop) if drop is not None else None, fws.data_ptr(), fws_bytes, stream())
     st.__dict__.update(args=a, keep=keep, am=am, B=B, S=S, T=T, R=R, mode=mode, x0=x0, acts=acts, bufs=bufs,
-                       feat_bf16=feat_bf16, y_img=y_img, masks_u8=masks_u8, W=W)
+                       feat_bf16=feat_bf16, y_img=y_img, masks_u8=masks_u8, W=W, drop=drop)
     return x0, outs, st
 
 
@@ -135,10 +149,11 @@ def encoder_backward(enc, arena, st, dout):
     ws_bytes = int(_lib.lib().uc2_encoder_bwd_workspace_bytes(B, S))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dout.device)
     dx0 = torch.empty((M, 768), dtype=BF16, device=dout.device)
+    dptr = C.byref(st.drop) if st.drop is not None else None
     sync = getattr(arena, "grad_sync", None)
     if sync is None or not sync.enabled:
-        call("uc2_encoder_bwd", st.x0.data_ptr(), st.am.data_ptr(), B, S, L, st.W, st.acts, G, dout.data_ptr(),
-             dx0.data_ptr(), ws.data_ptr(), ws_bytes, stream())
+        call("uc2_encoder_bwd_dropout", st.x0.data_ptr(), st.am.data_ptr(), B, S, L, st.W, st.acts, G, dout.data_ptr(),
+             dx0.data_ptr(), dptr, ws.data_ptr(), ws_bytes, stream())
     else:
         # Data parallel: run the stack in segments of layers (top first) and hand each finished slice of the
         # gradient arena to the NCCL stream while the next segment computes.
@@ -154,11 +169,11 @@ def encoder_backward(enc, arena, st, dout):
             lo = max(0, hi - seg)
             x_in = st.x0 if lo == 0 else st.bufs[lo - 1]["out"]
             d_lo = dx0 if lo == 0 else torch.empty((M, 768), dtype=BF16, device=dout.device)
-            call("uc2_encoder_bwd", x_in.data_ptr(), st.am.data_ptr(), B, S, hi - lo,
+            call("uc2_encoder_bwd_dropout", x_in.data_ptr(), st.am.data_ptr(), B, S, hi - lo,
                  C.cast(C.byref(st.W, lo * WS), C.POINTER(_lib.LayerWeights)),
                  C.cast(C.byref(st.acts, lo * AS), C.POINTER(_lib.LayerActs)),
                  C.cast(C.byref(G, lo * GS), C.POINTER(_lib.LayerGrads)),
-                 d_hi.data_ptr(), d_lo.data_ptr(), ws.data_ptr(), ws_bytes, stream())
+                 d_hi.data_ptr(), d_lo.data_ptr(), dptr, ws.data_ptr(), ws_bytes, stream())
             end = layers_end if hi == L else q0(hi)
             sync.ready(q0(lo), end)
             d_hi, hi = d_lo, lo

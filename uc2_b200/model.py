@@ -207,13 +207,25 @@ class UC2PreTrainedModel(nn.Module):
         a.sync_shadow()
         return a
 
-    def _dropout_check(self):
-        if self.training:
-            ps = [m.p for m in self.modules() if isinstance(m, nn.Dropout)]
-            if any(p > 0 for p in ps) and not getattr(self, "_uc2_warned_dropout", False):
-                warnings.warn("uc2_b200: dropout > 0 is not implemented in the fused kernels yet; running with p = 0 "
-                              "(call utils.set_dropout(model, 0) to silence)")
-                object.__setattr__(self, "_uc2_warned_dropout", True)
+    def _dropout_cfg(self):
+        """(p_hidden, p_attn, seed, counter) for this forward pass, or None.  The probabilities are read from the
+        nn.Dropout modules the reference declares (so utils.set_dropout / model.eval() act as usual); every
+        hidden-state dropout has to share one p and every attention dropout one p, as in every UC2 config."""
+        if not self.training:
+            return None
+        hid, att = set(), set()
+        for n, m in self.named_modules():
+            if isinstance(m, nn.Dropout):
+                (att if n.endswith("attention.self.dropout") else hid).add(float(m.p))
+        if len(hid) > 1 or len(att) > 1:
+            raise NotImplementedError("per-module dropout probabilities are not supported: hidden {} attention {}"
+                                      .format(sorted(hid), sorted(att)))
+        p_h, p_a = (hid.pop() if hid else 0.0), (att.pop() if att else 0.0)
+        if p_h == 0.0 and p_a == 0.0:
+            return None
+        c = getattr(self, "_uc2_drop_counter", 0) + 1
+        object.__setattr__(self, "_uc2_drop_counter", c)
+        return (p_h, p_a, int(torch.initial_seed()), c)
 
     @classmethod
     def from_pretrained(cls, config_file, state_dict, load_embedding_only=False, load_layer=None, *inputs, **kwargs):
@@ -313,7 +325,8 @@ class _EncoderModel(UC2PreTrainedModel):
         am = torch.ones(gather_index.shape, dtype=torch.long, device=gather_index.device)
         with torch.no_grad():
             x0, _, _ = Fn.encoder_forward(self, self._arena(), input_ids, self._pos(position_ids), img_feat,
-                                          img_pos_feat, am, gather_index, img_masks, save=False, embed_only=True)
+                                          img_pos_feat, am, gather_index, img_masks, save=False, embed_only=True,
+                                          dropout=_root_of(self)._dropout_cfg() if self.training else None)
         return x0
 
     def _pos(self, position_ids):
@@ -325,10 +338,10 @@ class _EncoderModel(UC2PreTrainedModel):
             raise NotImplementedError("explicit token type ids are not used by any UC2 call site and are not "
                                       "implemented (text = type 0, regions = type 1)")
         root = _root_of(self)
-        root._dropout_check()
         arena = self._arena()
         kw = dict(input_ids=input_ids, position_ids=position_ids, img_feat=img_feat, img_pos_feat=img_pos_feat,
-                  attention_mask=attention_mask, gather_index=gather_index, img_masks=img_masks)
+                  attention_mask=attention_mask, gather_index=gather_index, img_masks=img_masks,
+                  dropout=root._dropout_cfg() if self.training else None)
         if torch.is_grad_enabled():
             if output_all_encoded_layers:
                 raise NotImplementedError("output_all_encoded_layers=True is only available under torch.no_grad() "
