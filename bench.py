@@ -26,8 +26,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"          # both levels print NCCL's version banner to stdout; rank 0 prints ONE line
 
 from uc2_b200 import batch as UB  # noqa: E402
 from uc2_b200 import synth  # noqa: E402

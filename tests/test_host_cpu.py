@@ -140,6 +140,21 @@ assert torch.allclose(flat, exp), (flat[:5], exp[:5])
 flat2 = torch.ones(10) * (r + 1)
 s2 = D.GradSync(flat2); s2.enabled = False; s2.ready(0, 10); s2.finish()
 assert torch.equal(flat2, torch.ones(10) * (r + 1))
+# row-sparse exchange of a [12, 4] table at offset 8 of a flat buffer: rank r touched rows {1, 3+r, 3+r (dup), 7}
+flat3 = torch.zeros(8 + 12 * 4 + 5)
+flat3[:8] = r + 1.0
+tab = flat3[8:8 + 48].view(12, 4)
+ids = torch.tensor([7, 1, 3 + r, 3 + r])
+for i in set(ids.tolist()):
+    tab[i] = (r + 1) * (i + 1)
+flat3[-5:] = 10.0 * (r + 1)
+s3 = D.GradSync(flat3, bucket_bytes=16 * 4)
+s3.sparse_rows_table(8, 12, 4, ids)
+s3.finish()                                   # the rest of the buffer goes through the dense path
+exp3 = torch.zeros(12, 4)
+exp3[1] = (1 * 2 + 2 * 2) / 2.0; exp3[7] = (1 * 8 + 2 * 8) / 2.0; exp3[3] = 1 * 4 / 2.0; exp3[4] = 2 * 5 / 2.0
+assert torch.allclose(flat3[8:56].view(12, 4), exp3), flat3[8:56].view(12, 4)
+assert torch.allclose(flat3[:8], torch.full((8,), 1.5)) and torch.allclose(flat3[-5:], torch.full((5,), 15.0))
 t = [torch.ones(3) * (r + 1), torch.ones(2) * (r + 1)]
 D.all_reduce_and_rescale_tensors(t, 2.0)
 assert torch.allclose(t[0], torch.ones(3) * 0.75)

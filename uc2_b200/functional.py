@@ -220,7 +220,16 @@ def encoder_backward(enc, arena, st, dout):
             names.append(ip + "mask_embedding.weight")
     arena.touch(*names)
     if sync is not None and sync.enabled:
-        sync.ready(0, arena.offset[pre + "encoder.layer.0.attention.self.query.weight"])     # embeddings: last
+        q0_off = arena.offset[pre + "encoder.layer.0.attention.self.query.weight"]
+        wname = pre + "embeddings.word_embeddings.weight"
+        if (st.mode != 2 and arena.offset[wname] == 0 and getattr(sync, "allow_sparse", False)
+                and not getattr(arena, "word_emb_dense", False)):
+            # only token rows of the vocabulary table carry gradient: exchange those rows, not 768 MB of zeros
+            w_end = arena.numel[wname]
+            sync.sparse_rows_table(0, arena.shape[wname][0], arena.shape[wname][1], st.keep[0])
+            sync.ready(w_end, q0_off)
+        else:
+            sync.ready(0, q0_off)                                                        # embeddings: last
 
 
 class EncoderFn(torch.autograd.Function):
@@ -299,6 +308,8 @@ class LinearFn(torch.autograd.Function):
             _lib.gemm(x, dz, K, N, n, a_mn=True, b_mn=True, out_f32=arena.g(wname), accumulate=True, split_k=0)
         if big:
             call("uc2_cast_f32_bf16", dx32.data_ptr(), dx.data_ptr(), dx.numel(), stream())
+        if wname.endswith("embeddings.word_embeddings.weight"):
+            arena.word_emb_dense = True          # tied decoder: the vocabulary-table gradient is dense this step
         arena.touch(wname, *( [bname] if bname else []))
         return dx, None, None, None, None, None, None
 

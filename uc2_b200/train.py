@@ -53,6 +53,7 @@ class TrainStep(object):
         if D.size() > 1 and (self.sync is None or self.sync.flat.data_ptr() != arena.grad.data_ptr()):
             self.sync = D.GradSync(arena.grad, self.bucket_bytes)
             self.sync.layers_per_segment = self.layers_per_segment
+            self.sync.allow_sparse = self.accum == 1     # with accumulation earlier micro-steps touched other rows
             arena.grad_sync = self.sync
         return arena
 
@@ -69,6 +70,7 @@ class TrainStep(object):
         if last:
             if self.sync is not None:
                 self.sync.finish()
+            self.model._arena().word_emb_dense = False
             self.global_step += 1
             if self.lr_fn is not None:
                 lr = self.lr_fn(self.global_step)
