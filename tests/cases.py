@@ -101,3 +101,20 @@ def retrieval_case(n_img=10, caps_per_img=2, seed=21, vocab=SMALL_VOCAB, family=
     txt2img = {t: f"img{i // caps_per_img}" for i, t in enumerate(txt_ids)}
     img2txts = {f"img{j}": [txt_ids[j * caps_per_img + k] for k in range(caps_per_img)] for j in range(n_img)}
     return images, captions, txt_ids, txt2img, img2txts
+
+
+def batch_tlm(n=4, seed=12, vocab=SMALL_VOCAB, half_len=60, num_bb=100):
+    """BASELINE.json configs[4] (VTLM): <s> src </s> <s> tgt </s> with positions restarting at the second <s>
+    (data/mlm.py:420-428), both halves masked, + 100 regions: S = 2 * half_len + 2 + num_bb."""
+    items = _items(n, seed, vocab, "vlxlmr", txt_len=2 * half_len + 2, num_bb=num_bb)
+    for it in items:
+        ids = it["input_ids"]
+        ids[half_len] = 2          # </s> closing the source half
+        ids[half_len + 1] = 0      # <s> opening the target half
+    lab = synth.make_mlm_labels([it["input_ids"] for it in items], seed, mask_id=vocab - 1, vocab=vocab)
+    lab = [(m, l) for m, l in lab]
+    for (m, l), it in zip(lab, items):                      # never mask the inner specials
+        for k in (half_len, half_len + 1):
+            m[k] = it["input_ids"][k]
+            l[k] = -1
+    return B.collate_tlm(items, lab)

@@ -352,3 +352,32 @@ def test_dropout_training_mode_matches_oracle_with_same_masks(p_h, p_a):
         t2 = enc(db["input_ids"], None, db["img_feat"], db["img_pos_feat"], db["attn_masks"], db["gather_index"],
                  output_all_encoded_layers=False)
         assert not torch.equal(t1, t2)
+
+
+def test_vtlm_translation_pairs_cfg5_shape():
+    """BASELINE.json configs[4]: VTLM bilingual pretraining, 2 x 60-token translations + 100 regions (S = 222),
+    task 'tlm' with per-sample position ids that restart at the second <s>; loss and every gradient vs the oracle.
+    S = 222 also exercises the single-buffer per-head attention backward."""
+    from oracle import uc2_oracle as O
+    from uc2_b200.utils import set_dropout
+    cfg = cases.config(2)
+    m, sd = build("pretrain", cfg)
+    m.train()
+    set_dropout(m, 0)
+    b = cases.batch_tlm()
+    assert b["attn_masks"].size(1) == 222 and b["position_ids"].shape == b["input_ids"].shape
+    assert int(b["position_ids"][0, 61]) == 2 and int(b["position_ids"][0, 62]) == 3 and int(b["position_ids"][0, 0]) == 2
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    lref = O.forward_pretraining(sdg, O.Family("vlxlmr"), b, "tlm").mean()
+    lref.backward()
+    out = m(dev(b), task="tlm")
+    lgot = out.mean()
+    lgot.backward()
+    np.testing.assert_allclose(lgot.item(), lref.item(), rtol=LOSS_RTOL)
+    top = max(float(v.grad.norm()) for v in sdg.values() if v.grad is not None)
+    for n_, p_ in m.named_parameters():
+        gr = sdg[n_].grad
+        if gr is None or float(gr.norm()) < 1e-6 * top:
+            continue
+        rel = float((p_.grad.detach().cpu() - gr).norm() / gr.norm())
+        assert rel <= 2e-2, f"{n_}: relative gradient error {rel:.4f}"

@@ -98,6 +98,23 @@ def collate_mlm(items, labeled, pad_id=1):
     return batch
 
 
+def tlm_position_ids(input_ids, start=2):
+    """data/mlm.py:420-428 (VTLM): positions count up from 3 and restart at every <s> (id 0), so both halves of a
+    translation pair get the same position range."""
+    out, pos = [], start
+    for t in input_ids.tolist():
+        pos = start if t == 0 else pos + 1
+        out.append(pos)
+    return torch.tensor(out, dtype=torch.long)
+
+
+def collate_tlm(items, labeled, pad_id=1):
+    """xlmr_tlm_ni_dmasking_collate (data/mlm.py:803-842): as collate_mlm plus per-sample position ids padded with 1."""
+    batch = collate_mlm(items, labeled, pad_id)
+    batch["position_ids"] = pad_sequence([tlm_position_ids(m) for m, _ in labeled], batch_first=True, padding_value=1)
+    return batch
+
+
 def _mrm_common(items, img_masks, pad_id=1):
     batch, txt_lens, num_bbs = _common(items, pad_id)
     m = pad_sequence(img_masks, batch_first=True, padding_value=0).bool()
