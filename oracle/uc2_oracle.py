@@ -320,6 +320,17 @@ def forward_pretraining(sd, fam, batch, task, compute_loss=True, ot_pos_only=Fal
         lab = batch["txt_labels"]
         scores = mlm_head(sd, fam, masked_hidden(h, lab != -1))
         return F.cross_entropy(scores, lab[lab != -1], reduction="none") if compute_loss else scores
+    if task in ("mmxlm", "vmlm"):                                 # model.py:598-624
+        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"])
+        lab = batch["txt_labels"]
+        scores = mlm_head(sd, fam, masked_hidden(h, lab != -1))
+        return F.cross_entropy(scores, lab[lab != -1], reduction="none") if compute_loss else scores
+    if task in ("mmxlm-soft", "vmlm-soft"):                       # model.py:626-651
+        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"])
+        pred = mlm_head(sd, fam, masked_hidden(h, batch["tgt_masks"]))[:, torch.as_tensor(batch["valid_token_ids"])]
+        if not compute_loss:
+            return pred
+        return F.kl_div(F.log_softmax(pred, -1), batch["label_targets"], reduction="none")
     if task == "mrfr":
         h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"])
         pred = mrfr_head(sd, fam, masked_hidden(h, batch["img_mask_tgt"]))

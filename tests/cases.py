@@ -118,3 +118,33 @@ def batch_tlm(n=4, seed=12, vocab=SMALL_VOCAB, half_len=60, num_bb=100):
             m[k] = it["input_ids"][k]
             l[k] = -1
     return B.collate_tlm(items, lab)
+
+
+VALID_TOKEN_IDS = list(range(16))       # what tests/golden/ref_shims.py installs as VALID_XLMR_TOKEN_IDS
+
+
+def batch_mmxlm(n=6, seed=13, vocab=SMALL_VOCAB, family="vlxlmr", **kw):
+    """MRTM hard labels: masked words AND masked regions predict token ids (data/mlm.py:440-468)."""
+    items = _items(n, seed, vocab, family, **kw)
+    lab = synth.make_mlm_labels([it["input_ids"] for it in items], seed, mask_id=vocab - 1, vocab=vocab)
+    nbbs = [it["img_feat"].size(0) for it in items]
+    masks = synth.make_img_masks(nbbs, seed)
+    img_lab = []
+    for i, (nb, mk) in enumerate(zip(nbbs, masks)):
+        tok = torch.from_numpy(synth.det_randint(nb, 5, vocab, seed * 77 + i, 5).astype(np.int64))
+        img_lab.append(torch.where(mk, tok, torch.full_like(tok, -1)))
+    return B.collate_mmxlm(items, lab, masks, img_lab, pad_id=pad_id(family))
+
+
+def batch_mmxlm_soft(n=6, seed=14, vocab=SMALL_VOCAB, family="vlxlmr", **kw):
+    """MRTM soft labels: masked regions predict a distribution over the valid token ids (data/mlm.py:319-345)."""
+    items = _items(n, seed, vocab, family, **kw)
+    nbbs = [it["img_feat"].size(0) for it in items]
+    masks = synth.make_img_masks(nbbs, seed)
+    soft = []
+    for i, nb in enumerate(nbbs):
+        z = torch.from_numpy(synth.det_normal((nb, len(VALID_TOKEN_IDS)), seed * 91 + i, 2.0)).float()
+        soft.append(torch.softmax(z, -1))
+    b = B.collate_mmxlm_soft(items, masks, soft, pad_id=pad_id(family))
+    b["valid_token_ids"] = torch.tensor(VALID_TOKEN_IDS)
+    return b

@@ -111,6 +111,11 @@ def case_pretrain(family="vlxlmr"):
     b_mrc = cases.batch_mrc(family=family)
     run_task(m, b_mrc, "mrc-kl", out, "mrc-kl")
     run_task(m, b_mrc, "mrc", out, "mrc")
+    if family == "vlxlmr":                       # MRTM tasks exist for the VLXLMR family only (model.py:522-543)
+        run_task(m, cases.batch_mmxlm(), "mmxlm", out, "mmxlm")
+        b_soft = dict(cases.batch_mmxlm_soft())
+        b_soft.pop("valid_token_ids")           # the reference reads its module-level VALID_XLMR_TOKEN_IDS (shimmed)
+        run_task(m, b_soft, "vmlm-soft", out, "vmlm-soft")
     return out
 
 

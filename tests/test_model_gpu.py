@@ -159,14 +159,19 @@ def test_rank_loss_and_grads(golden):
 
 
 @pytest.mark.parametrize("family", ["vlxlmr", "uniter"])
-@pytest.mark.parametrize("task", ["mlm", "mrfr", "mrc-kl", "mrc", "itm"])
+@pytest.mark.parametrize("task", ["mlm", "mrfr", "mrc-kl", "mrc", "itm", "mmxlm", "vmlm-soft"])
 def test_pretraining_task(golden, family, task):
+    if family == "uniter" and task in ("mmxlm", "vmlm-soft"):
+        pytest.skip("the MRTM tasks exist for the VLXLMR family only (model/model.py:522-543)")
     g = golden("pretrain" if family == "vlxlmr" else "pretrain_uniter")
     cfg = cases.config(2, family=family)
     m, _ = build("pretrain", cfg, family)
     mk = {"mlm": cases.batch_mlm, "mrfr": cases.batch_mrfr, "mrc-kl": cases.batch_mrc, "mrc": cases.batch_mrc,
-          "itm": cases.batch_itm}[task]
-    b = dev(mk(family=family))
+          "itm": cases.batch_itm, "mmxlm": cases.batch_mmxlm, "vmlm-soft": cases.batch_mmxlm_soft}[task]
+    b = mk(family=family)
+    if task == "vmlm-soft":
+        m.valid_token_ids = b.pop("valid_token_ids")
+    b = dev(b)
     from uc2_b200.utils import set_dropout
     m.train()
     set_dropout(m, 0)

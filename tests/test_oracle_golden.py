@@ -51,6 +51,9 @@ def test_pretraining_tasks(golden, family):
     batches = {"itm": cases.batch_itm(family=family), "mlm": cases.batch_mlm(family=family),
                "mrfr": cases.batch_mrfr(family=family), "mrc-kl": cases.batch_mrc(family=family)}
     batches["mrc"] = batches["mrc-kl"]
+    if family == "vlxlmr":
+        batches["mmxlm"] = cases.batch_mmxlm()
+        batches["vmlm-soft"] = cases.batch_mmxlm_soft()
     # packed embedding + hidden states
     for tag in ("itm", "mrfr"):
         b = batches[tag]

@@ -144,6 +144,35 @@ def collate_mrc(items, img_masks, soft_labels, pad_id=1):
     return batch
 
 
+def collate_mmxlm(items, labeled, img_masks, img_token_labels, pad_id=1):
+    """xlmr_mmxlm_collate (data/mlm.py:887-934), tasks 'mmxlm' / 'vmlm' (MRTM): txt_labels live in PACKED coordinates,
+    cat(caption labels [tl], region token labels [nbb]) per sample (data/mlm.py:467), padded with -1; masked regions
+    are zeroed (_mask_img_feat) and flagged in img_masks."""
+    its = [dict(it, input_ids=m) for it, (m, _) in zip(items, labeled)]
+    batch, m = _mrm_common(its, img_masks, pad_id)
+    del batch["img_mask_tgt"]
+    batch["txt_labels"] = pad_sequence([torch.cat([l, r]) for (_, l), r in zip(labeled, img_token_labels)],
+                                       batch_first=True, padding_value=-1)
+    S = batch["attn_masks"].size(1)
+    if batch["txt_labels"].size(1) < S:
+        batch["txt_labels"] = torch.nn.functional.pad(batch["txt_labels"], (0, S - batch["txt_labels"].size(1)), value=-1)
+    batch["img_feat"] = batch["img_feat"].masked_fill(m.unsqueeze(-1), 0)
+    batch["n_masked"] = int((batch["txt_labels"] != -1).sum())
+    return batch
+
+
+def collate_mmxlm_soft(items, img_masks, img_token_soft_labels, pad_id=1):
+    """xlmr_mmxlm_softlabel_collate (data/mlm.py:936-1008), tasks 'mmxlm-soft' / 'vmlm-soft': tgt_masks marks the
+    masked regions in packed coordinates, label_targets = rows of the per-region token distributions at the masked
+    regions (_get_targets), row-major."""
+    batch, m = _mrm_common(items, img_masks, pad_id)
+    batch["tgt_masks"] = batch.pop("img_mask_tgt")
+    soft = pad_tensors(img_token_soft_labels, [s.size(0) for s in img_token_soft_labels])
+    batch["label_targets"] = soft[m].contiguous()
+    batch["img_feat"] = batch["img_feat"].masked_fill(m.unsqueeze(-1), 0)
+    return batch
+
+
 def to_device(batch, device, non_blocking=True):
     out = {}
     for k, v in batch.items():

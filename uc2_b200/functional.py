@@ -514,6 +514,28 @@ class SoftmaxLossFn(torch.autograd.Function):
         return dl, None, None, None
 
 
+class SelectColumnsFn(torch.autograd.Function):
+    """logits[:, cols] (model/model.py:643 `prediction[:, VALID_XLMR_TOKEN_IDS]`): pure index plumbing -- a column
+    gather forward, a column scatter backward; the output row pitch is padded like the logits'."""
+
+    @staticmethod
+    def forward(ctx, logits, cols):
+        n = logits.size(0)
+        out = torch.empty((n, _pad8(cols.numel())), dtype=logits.dtype, device=logits.device)[:, :cols.numel()]
+        torch.index_select(logits, 1, cols, out=out) if out.is_contiguous() else out.copy_(logits.index_select(1, cols))
+        ctx.save_for_backward(cols)
+        ctx.shape = (n, logits.size(1), logits.stride(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (cols,) = ctx.saved_tensors
+        n, Cc, ld = ctx.shape
+        d = torch.zeros((n, ld), dtype=dout.dtype, device=dout.device)[:, :Cc]
+        d.index_add_(1, cols, dout)
+        return d, None
+
+
 class MseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):

@@ -445,6 +445,7 @@ class _ForPretraining(UC2PreTrainedModel):
         self.region_classifier = RegionClassification(config.hidden_size, img_label_dim)
         self.itm_output = nn.Linear(config.hidden_size, 2)
         self.ot_pos_only = ot_pos_only
+        self.valid_token_ids = None           # VALID_XLMR_TOKEN_IDS of the '*-soft' MRTM tasks (see forward_mmxlm_soft)
         self.apply(self.init_weights)
         self.vocab_pad = 0
         _adopt(self)
@@ -510,9 +511,13 @@ class _ForPretraining(UC2PreTrainedModel):
         elif task.startswith("mrc"):
             return self.forward_mrc(input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index,
                                     batch["img_masks"], batch["img_mask_tgt"], batch["label_targets"], task, compute_loss)
-        elif task in ("mmxlm", "vmlm", "mmxlm-soft", "vmlm-soft"):
-            raise NotImplementedError(f"task {task!r} (MRTM label tables need the XLM-R tokenizer download, "
-                                      "model/const_variable.py:6) is outside the hot-path scope, see DESIGN.md")
+        elif task in ("mmxlm", "vmlm"):
+            return self.forward_mmxlm(input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index,
+                                      batch["img_masks"], batch["txt_labels"], compute_loss, batch["n_masked"])
+        elif task in ("mmxlm-soft", "vmlm-soft"):
+            return self.forward_mmxlm_soft(input_ids, position_ids, img_feat, img_pos_feat, attention_mask,
+                                           gather_index, batch["img_masks"], batch["tgt_masks"],
+                                           batch["label_targets"], compute_loss)
         else:
             raise ValueError("invalid task")
 
@@ -526,6 +531,37 @@ class _ForPretraining(UC2PreTrainedModel):
         if compute_loss:
             return Fn.SoftmaxLossFn.apply(scores, 0, txt_labels[mask], -100)
         return scores
+
+    def forward_mmxlm(self, input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index, img_masks,
+                      txt_labels, compute_loss=True, n_masked=None):
+        """MRTM with hard token labels (model/model.py:598-624): like MLM, but regions are masked too and
+        txt_labels covers the whole packed sequence."""
+        seq = self._enc(input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index,
+                        output_all_encoded_layers=False, img_masks=img_masks)
+        mask = txt_labels != -1
+        rows = Fn.MaskedRowsFn.apply(seq, mask, _count(mask, n_masked))
+        scores = self._mlm_scores(rows)
+        if compute_loss:
+            return Fn.SoftmaxLossFn.apply(scores, 0, txt_labels[mask], -100)
+        return scores
+
+    def forward_mmxlm_soft(self, input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index,
+                           img_masks, tgt_masks, label_targets, compute_loss=True):
+        """MRTM with soft token labels (model/model.py:626-651): vocabulary logits of the masked regions restricted
+        to `self.valid_token_ids` (the reference's VALID_XLMR_TOKEN_IDS, model/const_variable.py -- built from the
+        XLM-R tokenizer there; here a LongTensor / list the caller assigns), KL against token distributions."""
+        if getattr(self, "valid_token_ids", None) is None:
+            raise ValueError("set model.valid_token_ids (the reference's VALID_XLMR_TOKEN_IDS) before running "
+                             "the '*-soft' MRTM tasks")
+        seq = self._enc(input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index,
+                        output_all_encoded_layers=False, img_masks=img_masks)
+        rows = Fn.MaskedRowsFn.apply(seq, tgt_masks, int(label_targets.size(0)))
+        scores = self._mlm_scores(rows)
+        cols = torch.as_tensor(self.valid_token_ids, dtype=torch.long, device=scores.device)
+        pred = Fn.SelectColumnsFn.apply(scores, cols)
+        if compute_loss:
+            return Fn.SoftmaxLossFn.apply(pred, 1, label_targets, -1)
+        return pred
 
     def forward_mrfr(self, input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index, img_masks,
                      img_mask_tgt, feat_targets, compute_loss=True):
