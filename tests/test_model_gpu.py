@@ -386,3 +386,82 @@ def test_vtlm_translation_pairs_cfg5_shape():
             continue
         rel = float((p_.grad.detach().cpu() - gr).norm() / gr.norm())
         assert rel <= 2e-2, f"{n_}: relative gradient error {rel:.4f}"
+
+
+def test_text_only_and_image_only_modes():
+    """The other two embedding modes of UniterModel.forward (model.py:439-446): text only ('tlm-ni', img_feat None,
+    attention mask over the T text columns) with loss + gradients, and image only (input_ids None) forward."""
+    from oracle import uc2_oracle as O
+    from uc2_b200.utils import set_dropout
+    cfg = cases.config(2)
+    m, sd = build("pretrain", cfg)
+    m.train()
+    set_dropout(m, 0)
+    b = cases.batch_mlm(seed=31)
+    tl = (b["input_ids"] != 1).sum(1)
+    b_txt = dict(b, attn_masks=(torch.arange(b["input_ids"].size(1))[None, :] < tl[:, None]).long())
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    lref = O.forward_pretraining(sdg, O.Family("vlxlmr"), b_txt, "tlm-ni").mean()
+    lref.backward()
+    lgot = m(dev(b_txt), task="tlm-ni").mean()
+    lgot.backward()
+    np.testing.assert_allclose(lgot.item(), lref.item(), rtol=LOSS_RTOL)
+    top = max(float(v.grad.norm()) for v in sdg.values() if v.grad is not None)
+    for n_, p_ in m.named_parameters():
+        gr = sdg[n_].grad
+        if gr is None or float(gr.norm()) < 1e-6 * top:
+            assert float(p_.grad.norm()) < 1e-3 * top, n_          # image-side parameters: no gradient in this mode
+            continue
+        assert float((p_.grad.detach().cpu() - gr).norm() / gr.norm()) <= 2e-2, n_
+    # image only
+    nbb = (b["img_feat"].abs().sum(-1) > 0).sum(1)
+    am_img = (torch.arange(b["img_feat"].size(1))[None, :] < nbb[:, None]).long()
+    with torch.no_grad():
+        m.eval()
+        ref = O.encoder(sd, O.Family("vlxlmr"), None, None, b["img_feat"], b["img_pos_feat"], am_img)
+        db = dev(b)
+        got = m.roberta(None, None, db["img_feat"], db["img_pos_feat"], am_img.cuda(), output_all_encoded_layers=False)
+    valid = am_img.bool().numpy()
+    close(got.float().cpu().numpy()[valid], ref.numpy()[valid], what="image-only hidden states")
+
+
+def test_hard_negative_mining_step():
+    """VLXLMRForImageTextRetrievalHardNeg (model/itm.py:105-186): score 1 positive + candidates without grad, keep the
+    hard_size best negatives, train on those.  The mined indices must be the oracle's top-k (where its scores are
+    separated) and the loss on the mined batch must match the oracle's loss on the same sub-batch."""
+    from oracle import uc2_oracle as O
+    from uc2_b200 import itm
+    from uc2_b200.utils import set_dropout
+    cfg = cases.config(2)
+    sd = cases.weights(cfg, "retrieval")
+    m = itm.VLXLMRForImageTextRetrievalHardNeg(cfg, 2048, margin=0.2, hard_size=3)
+    m.load_state_dict(sd, strict=False)
+    m.cuda().train()
+    set_dropout(m, 0)
+    # one caption against 8 images (sample_from='t': text fixed, images vary); first image is the positive
+    items = cases._items(8, 55, cases.SMALL_VOCAB, "vlxlmr", txt_range=(9, 9), bb_range=(10, 30))
+    for it in items[1:]:
+        it["input_ids"] = items[0]["input_ids"]
+    b = B_collate(items)
+    loss = m(dev(b), sample_from="t", compute_loss=True)
+    assert tuple(loss.shape) == (1, 3)
+    loss.mean().backward()
+    assert float(m.rank_output.weight.grad.abs().sum()) > 0
+    with torch.no_grad():
+        sc = O.forward_retrieval(sd, O.Family("vlxlmr"), b, compute_loss=False).squeeze(1)
+    order = torch.argsort(sc[1:], descending=True) + 1
+    keep = torch.cat([torch.zeros(1, dtype=torch.long), order[:3]])
+    sub = {k: (v[keep] if torch.is_tensor(v) and v.dim() > 0 and v.size(0) == 8 else v) for k, v in b.items()}
+    L = int(sub["attn_masks"].sum(1).max())
+    sub["attn_masks"], sub["gather_index"] = sub["attn_masks"][:, :L], sub["gather_index"][:, :L]
+    sub["img_feat"], sub["img_pos_feat"] = sub["img_feat"][:, :L - 9], sub["img_pos_feat"][:, :L - 9]
+    sub["sample_size"] = 4
+    ref = O.forward_retrieval(sd, O.Family("vlxlmr"), sub)
+    gap = float((sc[order[2]] - sc[order[3]]).abs())
+    if gap > 2 * HID_TOL:                       # the mined set is unambiguous: losses must agree (order-insensitive)
+        np.testing.assert_allclose(np.sort(loss.detach().cpu().numpy().ravel()), np.sort(ref.numpy().ravel()), atol=1e-2)
+
+
+def B_collate(items):
+    from uc2_b200.batch import collate_itm_rank
+    return collate_itm_rank(items, len(items))
