@@ -202,6 +202,7 @@ attention_delta_kernel(const bf16* __restrict__ ctx, const bf16* __restrict__ dc
                        int B, int S) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    griddep_sync();
     if (row >= (long long)B * S) return;
     const int b = (int)(row / S), q = (int)(row % S);
 #pragma unroll
@@ -418,6 +419,7 @@ attention_fwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
     const uint32_t sV = sK + SP * 128;
     float* mbias = reinterpret_cast<float*>(smem + 3 * SP * 128);
     const long long base = (long long)b * S;
+    griddep_sync();
     load_tile_n(sQ, qkv, QKV_LD, base, h * HD, SP, S, blockDim.x);
     load_tile_n(sK, qkv, QKV_LD, base, HID + h * HD, SP, S, blockDim.x);
     load_tile_n(sV, qkv, QKV_LD, base, 2 * HID + h * HD, SP, S, blockDim.x);
@@ -513,6 +515,7 @@ attention_bwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
     };
     const int t = lane & 3, g = lane >> 2;
     int it = blockIdx.x, buf = 0;
+    griddep_sync();
     if (it < items) issue(it, 0);
     for (; it < items; it += gridDim.x) {
         const int b = it / NH, h = it % NH;
@@ -686,8 +689,8 @@ extern "C" UC2_API int uc2_attention_fwd_dropout(const void* qkv, const long lon
         const int SP = (S + 31) / 32 * 32;
         const int smem_bh = 3 * SP * 128 + SP * 4;
         if (int rc = set_smem(attention_fwd_bh_kernel, smem_bh)) return rc;
-        attention_fwd_bh_kernel<<<dim3(NH, B), bh_warps(S) * 32, smem_bh, (cudaStream_t)stream>>>(
-            (const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, SP, drop);
+        launch_pdl(attention_fwd_bh_kernel, dim3(NH, B), dim3(bh_warps(S) * 32), smem_bh, (cudaStream_t)stream, 1,
+                   (const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, SP, drop);
         return check_last("attention_fwd_bh_kernel");
     }
     const int smem = TILE * 128 + 2 * S_pad * 128 + S_pad * 4;
@@ -719,7 +722,8 @@ extern "C" UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long lon
     cudaStream_t s = (cudaStream_t)stream;
     const long long rows = (long long)B * S;
     ProfScope prof(s, 1, 10.0 * B * NH * (double)S * S * HD);      // 5 S x S x 64 products (7 computed)
-    attention_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>((const bf16*)ctx, (const bf16*)dctx, delta_ws, B, S);
+    launch_pdl(attention_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, 1, (const bf16*)ctx,
+               (const bf16*)dctx, delta_ws, B, S);
     if (int rc = check_last("attention_delta_kernel")) return rc;
     if (S <= 256) {
         const int SP = (S + 31) / 32 * 32;
@@ -728,8 +732,8 @@ extern "C" UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long lon
         if (int rc = set_smem(attention_bwd_bh_kernel, smem_bh)) return rc;
         const int items = B * NH;
         const int grid = items < num_sms() ? items : num_sms();
-        attention_bwd_bh_kernel<<<grid, bh_warps(S) * 32, smem_bh, s>>>((const bf16*)qkv, attn_mask, (const bf16*)dctx,
-                                                                       lse, delta_ws, (bf16*)dqkv, B, S, SP, nbuf, drop);
+        launch_pdl(attention_bwd_bh_kernel, dim3(grid), dim3(bh_warps(S) * 32), smem_bh, s, 1, (const bf16*)qkv, attn_mask,
+                   (const bf16*)dctx, lse, delta_ws, (bf16*)dqkv, B, S, SP, nbuf, drop);
         return check_last("attention_bwd_bh_kernel");
     }
     const int smem_dq = 2 * TILE * 128 + 2 * S_pad * 128 + S_pad * 4;

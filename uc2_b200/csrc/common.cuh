@@ -43,6 +43,35 @@ struct ProfScope {
     int idx_;
 };
 int require_sm100();
+bool pdl_enabled();      // programmatic dependent launch (off with UC2_NO_PDL=1)
+
+// Launch `kern` allowing it to start while the previous kernel of the stream is still draining (programmatic
+// dependent launch): its CTAs may become resident and run their prologue early, and MUST call griddep_wait()
+// before their first global access that depends on (or overwrites data of) the previous kernel.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     int cluster_x, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -53,6 +82,13 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
+
+// Programmatic dependent launch, device side: wait for the previous kernel of the stream (completion + memory
+// visibility), then let the next kernel's CTAs be scheduled as soon as every CTA of this grid got here or exited.
+__device__ __forceinline__ void griddep_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 constexpr int HID = 768;
 

@@ -328,6 +328,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    // everything above (barriers, TMEM, descriptor prefetch) may have run under the previous kernel's tail
+    griddep_sync();
 
     const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
     const int total_tiles = tiles_mn * p.split_k;
@@ -543,20 +545,7 @@ int launch(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
     const int workers = total < slots ? total : slots;
     {
         ProfScope prof(stream, 0, 2.0 * a.M * a.N * a.K);
-        if (CTAS == 1) {
-            kern<<<workers, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
-        } else {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(2 * workers);
-            cfg.blockDim = dim3(GEMM_THREADS);
-            cfg.dynamicSmemBytes = C::SMEM_BYTES;
-            cfg.stream = stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
-        }
+        launch_pdl(kern, dim3(CTAS * workers), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, CTAS, ta, tb, p);
     }
     return check_last("gemm_bf16_kernel");
 }

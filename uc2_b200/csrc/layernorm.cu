@@ -41,6 +41,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma
                      float eps, bf16* __restrict__ y, float* __restrict__ y32, long long rows) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    griddep_sync();
     if (row >= rows) return;
     float v[VPL];
     load_row<F32>(x, row, lane, v);
@@ -91,6 +92,7 @@ layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, co
         ptx::fence_proxy_async();
     }
     __syncthreads();
+    griddep_sync();
     const long long stride = (long long)gridDim.x * LN_WARPS;
     const long long first = (long long)blockIdx.x * LN_WARPS + warp;
     auto issue = [&](long long row, int s) {      // lane 0 only
@@ -175,6 +177,7 @@ layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, co
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, long long rows, int cols, float* __restrict__ out,
                    int row_chunk) {
+    griddep_sync();
     const int cg = blockIdx.x * 256 + (threadIdx.x & 31) * 8;      // 8 consecutive columns per thread
     const int rsub = threadIdx.x >> 5;                              // 8 row phases
     const long long r0 = (long long)blockIdx.y * row_chunk;
@@ -216,11 +219,11 @@ extern "C" UC2_API int uc2_layernorm_fwd(const void* x, int x_is_f32, const floa
                 "layernorm_fwd: pointers must be 16-byte aligned");
     const unsigned blocks = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
     if (x_is_f32)
-        layernorm_fwd_kernel<true><<<blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, (bf16*)y_bf16,
-                                                                                      y_f32, rows);
+        launch_pdl(layernorm_fwd_kernel<true>, dim3(blocks), dim3(LN_WARPS * 32), 0, (cudaStream_t)stream, 1, x, gamma,
+                   beta, eps, (bf16*)y_bf16, y_f32, rows);
     else
-        layernorm_fwd_kernel<false><<<blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, (bf16*)y_bf16,
-                                                                                       y_f32, rows);
+        launch_pdl(layernorm_fwd_kernel<false>, dim3(blocks), dim3(LN_WARPS * 32), 0, (cudaStream_t)stream, 1, x, gamma,
+                   beta, eps, (bf16*)y_bf16, y_f32, rows);
     return check_last("layernorm_fwd_kernel");
 }
 
@@ -248,12 +251,12 @@ extern "C" UC2_API int uc2_layernorm_bwd_dropout(const void* x, int x_is_f32, co
     const int smem = LN_WARPS * LN_STAGES * ((x_is_f32 ? HID * 4 : HID * 2) + HID * 2);
     if (x_is_f32) {
         UC2_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        layernorm_bwd_kernel<true><<<(unsigned)blocks, LN_WARPS * 32, smem, (cudaStream_t)stream>>>(
-            x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows, (bf16*)dx_masked, drop);
+        launch_pdl(layernorm_bwd_kernel<true>, dim3((unsigned)blocks), dim3(LN_WARPS * 32), smem, (cudaStream_t)stream, 1,
+                   x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows, (bf16*)dx_masked, drop);
     } else {
         UC2_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        layernorm_bwd_kernel<false><<<(unsigned)blocks, LN_WARPS * 32, smem, (cudaStream_t)stream>>>(
-            x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows, (bf16*)dx_masked, drop);
+        launch_pdl(layernorm_bwd_kernel<false>, dim3((unsigned)blocks), dim3(LN_WARPS * 32), smem, (cudaStream_t)stream, 1,
+                   x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows, (bf16*)dx_masked, drop);
     }
     return check_last("layernorm_bwd_kernel");
 }
@@ -268,7 +271,7 @@ extern "C" UC2_API int uc2_colsum_bf16(const void* x, long long ld, long long ro
     long long row_chunk = (rows + row_blocks - 1) / row_blocks;
     if (row_chunk < 64) row_chunk = 64;
     row_blocks = (int)((rows + row_chunk - 1) / row_chunk);
-    colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, rows, cols,
-                                                                                      out, (int)row_chunk);
+    launch_pdl(colsum_bf16_kernel, dim3(col_blocks, row_blocks), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x,
+               ld, rows, cols, out, (int)row_chunk);
     return check_last("colsum_bf16_kernel");
 }

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -50,6 +51,15 @@ int num_sms() {
     int sms = 148, cc = 0;
     dev_query(&sms, &cc);
     return sms;
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("UC2_NO_PDL");
+        on = (e && e[0] == '1') ? 0 : 1;
+    }
+    return on == 1;
 }
 
 int require_sm100() {
