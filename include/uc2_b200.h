@@ -88,6 +88,7 @@ typedef struct {
      * BertOutput (model/layer.py:113, 154).  keep(m, n) <=> (lowbias32((m * N + n) ^ drop_key) >> 16) >= drop_thresh;
      * kept values are multiplied by drop_scale.  drop_thresh = 0 disables it (uc2_b200/dropout.py has the rules). */
     unsigned int drop_key; unsigned int drop_thresh; float drop_scale;
+    int tail_split;   /* 0 = auto (split the tiles of a partial last round into column slices); 1 = never */
 } uc2_gemm_args;
 
 UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream);

@@ -22,7 +22,7 @@ class GemmArgs(C.Structure):
                 ("aux", P), ("ld_aux", LL), ("act", I), ("out_bf16", P), ("ld_out", LL),
                 ("out_pre", P), ("ld_pre", LL), ("out_f32", P), ("ld_f32", LL),
                 ("accumulate", I), ("split_k", I), ("block_n", I), ("residual_f32", I), ("ctas", I),
-                ("drop_key", C.c_uint), ("drop_thresh", C.c_uint), ("drop_scale", F)]
+                ("drop_key", C.c_uint), ("drop_thresh", C.c_uint), ("drop_scale", F), ("tail_split", I)]
 
 
 class EmbedArgs(C.Structure):
@@ -163,7 +163,7 @@ def launch_count():
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None, residual=None, aux=None,
          act=ACT_NONE, out_bf16=None, out_pre=None, out_f32=None, accumulate=False, split_k=1, block_n=0,
-         ld_out=None, ld_res=None, ctas=0, drop=None):
+         ld_out=None, ld_res=None, ctas=0, drop=None, tail_split=0):
     """D[M,N] = A[M,K] @ B[N,K]^T with the fused epilogue described in include/uc2_b200.h."""
     g = GemmArgs()
     g.a, g.lda, g.a_mn = a.data_ptr(), (lda if lda is not None else a.stride(0)), int(a_mn)
@@ -183,6 +183,7 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None
     if out_f32 is not None:
         g.out_f32, g.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
     g.accumulate, g.split_k, g.block_n, g.ctas = int(accumulate), split_k, block_n, ctas
+    g.tail_split = tail_split
     if drop is not None:
         g.drop_key, g.drop_thresh, g.drop_scale = drop
     check(lib().uc2_gemm_bf16(C.byref(g), stream()), "gemm")

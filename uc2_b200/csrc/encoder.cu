@@ -36,7 +36,7 @@ int run(cudaStream_t s, const G& g) {
     a.aux = g.aux; a.ld_aux = g.ld_aux; a.act = g.act; a.out_bf16 = g.out_bf16; a.ld_out = g.ld_out;
     a.out_pre = g.out_pre; a.ld_pre = g.ld_pre; a.out_f32 = g.out_f32; a.ld_f32 = g.ld_f32;
     a.accumulate = g.accumulate; a.split_k = g.split_k; a.block_n = 0; a.residual_f32 = g.res_f32; a.ctas = 0;
-    a.drop_key = g.drop.key; a.drop_thresh = g.drop.thresh; a.drop_scale = g.drop.scale;
+    a.drop_key = g.drop.key; a.drop_thresh = g.drop.thresh; a.drop_scale = g.drop.scale; a.tail_split = 0;
     return uc2_gemm_bf16(&a, s);
 }
 

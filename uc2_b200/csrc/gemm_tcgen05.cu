@@ -59,7 +59,33 @@ struct GemmParams {
     int accumulate;
     int vec_ok;   // leading dimensions / pointers allow 32-byte row-slice access -> vector epilogue
     DropCfg drop; // dropout on (acc + bias) before the residual add (BertSelfOutput / BertOutput, layer.py:113,154)
+    // Tail split: tiles [0, tail_start) are full BLOCK_N-wide tiles; each of the remaining tiles_mn - tail_start
+    // tiles (the partial last round of the persistent workers) is cut into tail_split column slices so that round
+    // costs ~1/tail_split of a full one (19200 tokens = 75 row blocks on 74 CTA pairs would otherwise pay a whole
+    // extra round for 1-4 % of the work).  tail_split == 1: off.
+    int tail_start, tail_split;
 };
+
+struct TileCoord { int m_blk, n0, width, split; };
+
+template <int BLOCK_N>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int tiles_mn) {
+    TileCoord c;
+    int base = t;
+    c.width = BLOCK_N;
+    int sub = 0;
+    if (p.tail_split > 1 && t >= p.tail_start) {
+        const int r = t - p.tail_start;
+        base = p.tail_start + r / p.tail_split;
+        sub = r % p.tail_split;
+        c.width = BLOCK_N / p.tail_split;
+    }
+    c.split = base / tiles_mn;
+    const int mn = base % tiles_mn;
+    c.m_blk = mn / p.num_n_blocks;
+    c.n0 = (mn % p.num_n_blocks) * BLOCK_N + sub * c.width;
+    return c;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act, float aux) {
     if (act == UC2_ACT_GELU) return gelu_erf(v);
@@ -141,7 +167,8 @@ __device__ __noinline__ void epilogue_scalar_row(const GemmParams& p, const floa
 // the shared-memory carve-out is the whole 227 KB).
 template <int BLOCK_N, int EX, int CTAS, int MODE>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc, int lane, int half, long long grow,
-                                              int ncol0, uint32_t tfull, uint32_t tfull_phase, uint32_t tempty) {
+                                              int ncol0, int ncols, uint32_t tfull, uint32_t tfull_phase,
+                                              uint32_t tempty) {
     using F = Epi<MODE>;
     constexpr int MY = BLOCK_N / 64;                 // chunks per warp: 1, 2 or 4
     constexpr int G = MY < 2 ? MY : 2;               // chunks per group
@@ -156,7 +183,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
 #pragma unroll
             for (int ii = 0; ii < G; ++ii) {
                 const int col0 = ncol0 + (2 * (g0 + ii) + half) * EPI_COLS;
-                if (p.vec_ok && col0 + EPI_COLS <= p.N && row_ok) {
+                if (p.vec_ok && col0 + EPI_COLS <= p.N && row_ok && (2 * (g0 + ii) + half) * EPI_COLS < ncols) {
                     const uint8_t* src = EX == 2
                         ? reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(exb) + grow * ld_ex + col0)
                         : reinterpret_cast<const uint8_t*>(exb + grow * ld_ex + col0);
@@ -175,9 +202,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int col0 = ncol0 + c * EPI_COLS + h * 16;
+                const bool in_tile = c * EPI_COLS < ncols;          // narrow tail tiles use the first columns only
                 uint32_t r[16];
-                ptx::tmem_ld_32x16(tacc + c * EPI_COLS + h * 16, r);
-                ptx::tmem_wait_ld();
+                if (in_tile) {
+                    ptx::tmem_ld_32x16(tacc + c * EPI_COLS + h * 16, r);
+                    ptx::tmem_wait_ld();
+                }
                 if (g0 + ii == MY - 1 && h == 1) {
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp (relaxed arrive:
                     // nothing in generic memory is published here, and a release at cluster scope would make the
@@ -189,7 +219,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                         else ptx::mbar_arrive(tempty);
                     }
                 }
-                if (col0 >= p.N || !row_ok) continue;
+                if (!in_tile || col0 >= p.N || !row_ok) continue;
                 const uint32_t* ex = pf + ii * W + h * (W / 2);
                 if (p.vec_ok && ncol0 + (c + 1) * EPI_COLS <= p.N) {
                     float v[16];
@@ -279,7 +309,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
 template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_b_tail, const GemmParams p) {
     using C = Cfg<BLOCK_N, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -332,7 +362,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     griddep_sync();
 
     const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
-    const int total_tiles = tiles_mn * p.split_k;
+    const int total_tiles = p.tail_split > 1 ? p.tail_start + (tiles_mn - p.tail_start) * p.tail_split
+                                             : tiles_mn * p.split_k;
 
     if (warp_idx == 0) {
         // ===================================== TMA producer =====================================
@@ -340,20 +371,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int t = unit; t < total_tiles; t += num_units) {
-                const int n_blk = t % p.num_n_blocks;
-                const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
-                const int split = t / tiles_mn;
-                const int kb0 = split * p.k_blocks_per_split;
+                const TileCoord tc = decode_tile<BLOCK_N>(p, t, tiles_mn);
+                const int kb0 = tc.split * p.k_blocks_per_split;
                 const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
-                const int m0 = (m_blk * CTAS + (int)cta_rank) * BLOCK_M;
-                const int n0 = n_blk * BLOCK_N + (int)cta_rank * C::B_ROWS;
+                const int m0 = (tc.m_blk * CTAS + (int)cta_rank) * BLOCK_M;
+                const int b_rows = tc.width / CTAS;                       // B rows (n) this CTA stages for the tile
+                const int n0 = tc.n0 + (int)cta_rank * b_rows;
+                const bool narrow = tc.width != BLOCK_N;
+                const uint32_t stage_tx = (C::A_BYTES + b_rows * BLOCK_K * 2) * CTAS;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                     const uint32_t sb = sa + C::A_BYTES;
                     // the pair's loads all report to the leader's barrier, which expects both CTAs' bytes
                     const uint32_t fb = CTAS == 2 ? ptx::map_to_cta(full_bar(stage), 0) : full_bar(stage);
-                    if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES * CTAS);
+                    if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), stage_tx);
                     auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
                         if (CTAS == 2) ptx::tma_load_2d_pair(dst, m, fb, c0, c1);
                         else ptx::tma_load_2d(dst, m, fb, c0, c1);
@@ -365,10 +397,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int j = 0; j < BLOCK_M / 64; ++j) load(sa + j * 8192, &tmap_a, m0 + j * 64, kb * BLOCK_K);
                     }
                     if (!B_MN) {
-                        load(sb, &tmap_b, kb * BLOCK_K, n0);
+                        load(sb, narrow ? &tmap_b_tail : &tmap_b, kb * BLOCK_K, n0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < C::B_ROWS / 64; ++j) load(sb + j * 8192, &tmap_b, n0 + j * 64, kb * BLOCK_K);
+                        for (int j = 0; j < C::B_ROWS / 64; ++j)
+                            if (j * 64 < b_rows) load(sb + j * 8192, &tmap_b, n0 + j * 64, kb * BLOCK_K);
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -387,9 +420,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int t = unit; t < total_tiles; t += num_units) {
-                const int split = t / tiles_mn;
-                const int kb0 = split * p.k_blocks_per_split;
+                const TileCoord tc = decode_tile<BLOCK_N>(p, t, tiles_mn);
+                const int kb0 = tc.split * p.k_blocks_per_split;
                 const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+                const uint32_t idesc_t = tc.width == BLOCK_N ? idesc
+                                                             : ptx::idesc_bf16_f32(BLOCK_M * CTAS, tc.width, A_MN, B_MN);
                 if (CTAS == 2) ptx::mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
                 else ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 ptx::tc_fence_after();
@@ -404,8 +439,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const uint64_t da = ptx::smem_desc_sw128(sa + k * A_KSTEP, A_LBO, 1024u);
                         const uint64_t db = ptx::smem_desc_sw128(sb + k * B_KSTEP, B_LBO, 1024u);
                         const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
-                        if (CTAS == 2) ptx::umma_bf16_pair(d_tmem, da, db, idesc, accum);
-                        else ptx::umma_bf16(d_tmem, da, db, idesc, accum);
+                        if (CTAS == 2) ptx::umma_bf16_pair(d_tmem, da, db, idesc_t, accum);
+                        else ptx::umma_bf16(d_tmem, da, db, idesc_t, accum);
                     }
                     // frees the smem slot (in both CTAs of a pair) once these MMAs retire
                     if (CTAS == 2) ptx::umma_commit_pair(empty_bar(stage));
@@ -427,21 +462,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = unit; t < total_tiles; t += num_units) {
-            const int n_blk = t % p.num_n_blocks;
-            const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
+            const TileCoord tc = decode_tile<BLOCK_N>(p, t, tiles_mn);
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-            const long long grow = (long long)(m_blk * CTAS + (int)cta_rank) * BLOCK_M + q * 32 + lane;
-            const int ncol0 = n_blk * BLOCK_N;
+            const long long grow = (long long)(tc.m_blk * CTAS + (int)cta_rank) * BLOCK_M + q * 32 + lane;
+            const int ncol0 = tc.n0;
+            const int ncols = tc.width;
             const uint32_t te = CTAS == 2 ? ptx::map_to_cta(tempty_bar(acc), 0) : tempty_bar(acc);
             if (MODE != 0)
-                epilogue_tile<BLOCK_N, Epi<MODE>::ex_kind, CTAS, MODE>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc),
-                                                                       acc_phase, te);
+                epilogue_tile<BLOCK_N, Epi<MODE>::ex_kind, CTAS, MODE>(p, tacc, lane, half, grow, ncol0, ncols,
+                                                                       tfull_bar(acc), acc_phase, te);
             else if (ex_kind == 0)
-                epilogue_tile<BLOCK_N, 0, CTAS, 0>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
+                epilogue_tile<BLOCK_N, 0, CTAS, 0>(p, tacc, lane, half, grow, ncol0, ncols, tfull_bar(acc), acc_phase, te);
             else if (ex_kind == 1)
-                epilogue_tile<BLOCK_N, 1, CTAS, 0>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
+                epilogue_tile<BLOCK_N, 1, CTAS, 0>(p, tacc, lane, half, grow, ncol0, ncols, tfull_bar(acc), acc_phase, te);
             else
-                epilogue_tile<BLOCK_N, 2, CTAS, 0>(p, tacc, lane, half, grow, ncol0, tfull_bar(acc), acc_phase, te);
+                epilogue_tile<BLOCK_N, 2, CTAS, 0>(p, tacc, lane, half, grow, ncol0, ncols, tfull_bar(acc), acc_phase, te);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
@@ -524,7 +559,7 @@ int worker_slots(cudaError_t* err) {
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS, int MODE = 0>
-int launch(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
+int launch(const uc2_gemm_args& a, const GemmParams& p_in, cudaStream_t stream) {
     using C = Cfg<BLOCK_N, CTAS>;
     static_assert(C::STAGES >= 3, "pipeline too shallow");
     static_assert(CTAS == 1 || C::B_ROWS % 64 == 0, "a CTA pair needs BLOCK_N >= 128");
@@ -541,11 +576,33 @@ int launch(const uc2_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
     if (!B_MN) rc = make_tmap(&tb, a.b, a.N, a.K, a.ldb, C::B_ROWS);
     else       rc = make_tmap(&tb, a.b, a.K, a.N, a.ldb, BLOCK_K);
     if (rc) return rc;
-    const int total = p.num_m_blocks * p.num_n_blocks * p.split_k;
+    GemmParams p = p_in;
+    CUtensorMap tb_tail = tb;
+    const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+    p.tail_start = tiles_mn;
+    p.tail_split = 1;
+    if (CTAS == 2 && BLOCK_N == 256 && p.split_k == 1 && a.tail_split != 1) {
+        // the partial last round of the persistent pairs: cut its tiles into column slices (see GemmParams)
+        const int full = tiles_mn / slots * slots, rem = tiles_mn - full;
+        if (full > 0 && rem > 0) {
+            int s = 1;
+            if (rem * 2 <= slots) s = 2;
+            if (!B_MN && rem * 4 <= slots) s = 4;                 // MN-major B boxes are 64 columns wide: halves only
+            if (s > 1) {
+                p.tail_start = full;
+                p.tail_split = s;
+                if (!B_MN) {
+                    rc = make_tmap(&tb_tail, a.b, a.N, a.K, a.ldb, C::B_ROWS / s);
+                    if (rc) return rc;
+                }
+            }
+        }
+    }
+    const int total = p.tail_split > 1 ? p.tail_start + (tiles_mn - p.tail_start) * p.tail_split : tiles_mn * p.split_k;
     const int workers = total < slots ? total : slots;
     {
         ProfScope prof(stream, 0, 2.0 * a.M * a.N * a.K);
-        launch_pdl(kern, dim3(CTAS * workers), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, CTAS, ta, tb, p);
+        launch_pdl(kern, dim3(CTAS * workers), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, CTAS, ta, tb, tb_tail, p);
     }
     return check_last("gemm_bf16_kernel");
 }
