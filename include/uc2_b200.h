@@ -283,6 +283,15 @@ UC2_API int uc2_rank_loss_bwd(const float* scores, const float* dloss, float* ds
 UC2_API int uc2_softmax_loss(const float* logits, long long ld, long long rows, int C, int kind,
                              const long long* targets, long long ignore_index, const float* soft_targets, float* loss,
                              const float* dloss, float* dlogits, float* lse_out, void* stream);
+/* Large-vocabulary form of kind 0 for the tied MLM decoder (model/layer.py:257-265 + model/model.py:592-596): forward
+ * is one pass per row (online max / sum) and also returns the row log-sum-exp; backward reads lse instead of
+ * recomputing it and writes d(logits) as the bf16 matrix (row pitch ld_out elements) the decoder's dgrad / wgrad
+ * GEMMs consume. */
+UC2_API int uc2_ce_loss_fwd(const float* logits, long long ld, long long rows, int C, const long long* targets,
+                            long long ignore_index, float* loss, float* lse, void* stream);
+UC2_API int uc2_ce_loss_bwd_bf16(const float* logits, long long ld, long long rows, int C, const long long* targets,
+                                 long long ignore_index, const float* dloss, const float* lse, void* dlogits_bf16,
+                                 long long ld_out, void* stream);
 /* F.mse_loss(reduction='none') model/model.py:684-685 and its backward */
 UC2_API int uc2_mse(const float* pred, const float* tgt, float* loss, const float* dloss, float* dpred, long long n,
                     void* stream);

@@ -100,6 +100,8 @@ _SIGS = {
     "uc2_rank_loss_bwd": [P, P, P, I, I, F, P],
     "uc2_softmax_loss": [P, LL, LL, I, I, P, LL, P, P, P, P, P, P],
     "uc2_mse": [P, P, P, P, P, LL, P],
+    "uc2_ce_loss_fwd": [P, LL, LL, I, P, LL, P, P, P],
+    "uc2_ce_loss_bwd_bf16": [P, LL, LL, I, P, LL, P, P, P, LL, P],
     "uc2_mask_scan": [P, LL, P, P, I, P],
     "uc2_gather_rows": [P, P, P, I, I, P, I, P],
     "uc2_scatter_rows_add": [P, P, P, I, I, P, I, P],

@@ -159,6 +159,82 @@ softmax_loss_kernel(const float* __restrict__ logits, long long ld, int C, int k
     }
 }
 
+// Large-vocabulary cross entropy (the tied MLM decoder: rows x 250 002 fp32 logits, 1 MB per row).
+// Forward: ONE pass over the row (online max / sum with 16-byte loads), writes loss and the row's log-sum-exp.
+// Backward: one pass, reads the logits once more and writes d(logits) directly as the bf16, 8-element-pitched
+// operand the dgrad / wgrad GEMMs consume (no fp32 d(logits) tensor, no separate cast kernel).
+constexpr int CE_THREADS = 512;
+
+__device__ __forceinline__ void online_add(float& m, float& s, float x) {
+    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
+    else s += __expf(x - m);
+}
+
+__global__ void __launch_bounds__(CE_THREADS)
+ce_loss_fwd_kernel(const float* __restrict__ logits, long long ld, int C, const long long* __restrict__ targets,
+                   long long ignore_index, float* __restrict__ loss, float* __restrict__ lse_out) {
+    __shared__ float red_m[CE_THREADS / 32], red_s[CE_THREADS / 32];
+    const long long r = blockIdx.x;
+    const float* x = logits + r * ld;
+    float m = -INFINITY, s = 0.f;
+    const int C4 = ((ld % 4) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) ? C / 4 : 0;
+    for (int i = threadIdx.x; i < C4; i += CE_THREADS) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float vm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (vm > m) { s *= __expf(m - vm); m = vm; }
+        s += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+    }
+    for (int c = C4 * 4 + threadIdx.x; c < C; c += CE_THREADS) online_add(m, s, x[c]);
+    // combine (m, s) pairs: warp, then block
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        const float mm = fmaxf(m, m2);
+        s = (m == -INFINITY ? 0.f : s * __expf(m - mm)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mm));
+        m = mm;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red_m[warp] = m; red_s[warp] = s; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float M = red_m[0], S = red_s[0];
+        for (int w = 1; w < CE_THREADS / 32; ++w) {
+            const float mm = fmaxf(M, red_m[w]);
+            S = (M == -INFINITY ? 0.f : S * __expf(M - mm)) + (red_m[w] == -INFINITY ? 0.f : red_s[w] * __expf(red_m[w] - mm));
+            M = mm;
+        }
+        const float lse = M + logf(S);
+        if (lse_out) lse_out[r] = lse;
+        const long long t = targets[r];
+        if (loss) loss[r] = (t == ignore_index) ? 0.f : lse - x[t];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ce_loss_bwd_kernel(const float* __restrict__ logits, long long ld, int C, const long long* __restrict__ targets,
+                   long long ignore_index, const float* __restrict__ dloss, const float* __restrict__ lse,
+                   bf16* __restrict__ dlogits, long long ld_out) {
+    const long long r = blockIdx.y;
+    const float* x = logits + r * ld;
+    bf16* d = dlogits + r * ld_out;
+    const long long t = targets[r];
+    const float g = (t == ignore_index) ? 0.f : dloss[r];
+    const float l = lse[r];
+    const bool vec = (ld % 4) == 0 && (ld_out % 4) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(dlogits) & 7) == 0;
+    const int c0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (c0 >= C) return;
+    if (vec && c0 + 4 <= C) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + c0));
+        float o[4] = {g * __expf(v.x - l), g * __expf(v.y - l), g * __expf(v.z - l), g * __expf(v.w - l)};
+        if (t >= c0 && t < c0 + 4) o[t - c0] -= g;
+        *reinterpret_cast<uint2*>(d + c0) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    } else {
+        for (int c = c0; c < C && c < c0 + 4; ++c)
+            d[c] = __float2bfloat16(g * (__expf(x[c] - l) - (c == t ? 1.f : 0.f)));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // order-exact masked-row compaction (hidden[mask], model/model.py:653-657), no host sync:
 //   pass 1 (one CTA): exclusive scan of the mask in row-major (b, j) order -> index list + count
@@ -321,6 +397,30 @@ extern "C" UC2_API int uc2_softmax_loss(const float* logits, long long ld, long 
     softmax_loss_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, C, kind, targets, ignore_index,
                                                                          soft_targets, loss, dloss, dlogits, lse_out);
     return check_last("softmax_loss_kernel");
+}
+
+extern "C" UC2_API int uc2_ce_loss_fwd(const float* logits, long long ld, long long rows, int C,
+                                       const long long* targets, long long ignore_index, float* loss, float* lse,
+                                       void* stream) {
+    if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(logits && targets && lse && rows >= 0 && C > 0 && ld >= C, UC2_ERR_ARG, "ce_loss_fwd: bad args");
+    if (rows == 0) return UC2_OK;
+    ce_loss_fwd_kernel<<<(unsigned)rows, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ld, C, targets, ignore_index,
+                                                                              loss, lse);
+    return check_last("ce_loss_fwd_kernel");
+}
+
+extern "C" UC2_API int uc2_ce_loss_bwd_bf16(const float* logits, long long ld, long long rows, int C,
+                                            const long long* targets, long long ignore_index, const float* dloss,
+                                            const float* lse, void* dlogits_bf16, long long ld_out, void* stream) {
+    if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(logits && targets && dloss && lse && dlogits_bf16 && rows >= 0 && C > 0 && ld >= C && ld_out >= C,
+                UC2_ERR_ARG, "ce_loss_bwd: bad args");
+    UC2_REQUIRE(rows < 65536, UC2_ERR_UNSUPPORTED, "ce_loss_bwd: at most 65535 rows per call");
+    if (rows == 0) return UC2_OK;
+    ce_loss_bwd_kernel<<<dim3((C + 1023) / 1024, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
+        logits, ld, C, targets, ignore_index, dloss, lse, (bf16*)dlogits_bf16, ld_out);
+    return check_last("ce_loss_bwd_kernel");
 }
 
 extern "C" UC2_API int uc2_mask_scan(const unsigned char* mask, long long n, int* index, int* count, int capacity,

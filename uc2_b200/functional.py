@@ -287,31 +287,74 @@ class LinearFn(torch.autograd.Function):
         if n == 0:
             return torch.zeros_like(x), None, None, None, None, None, None
         dy = _as_bf16_rows(dy)
-        Wm = arena.s(wname)
         if act == _lib.ACT_GELU:
             dz = _gelu_bwd(dy, pre)                   # dz = dy * gelu'(pre)
         elif act == _lib.ACT_NONE:
             dz = dy
         else:
             raise RuntimeError("LinearFn.backward: unsupported activation")
-        if bname:
-            call("uc2_colsum_bf16", dz.data_ptr(), dz.stride(0), n, N, arena.gp(bname), stream())
-        big = N > 8192       # vocabulary-sized contraction: split it over the SMs, accumulate in fp32
-        dx32 = torch.zeros((n, K), dtype=F32, device=x.device) if big else None
-        dx = torch.empty((n, K), dtype=BF16, device=x.device)
-        okw = dict(out_f32=dx32, accumulate=True, split_k=0) if big else dict(out_bf16=dx)
-        if not transposed:
-            _lib.gemm(dz, Wm, n, K, N, b_mn=True, **okw)                             # dx = dz W
-            _lib.gemm(dz, x, N, K, n, a_mn=True, b_mn=True, out_f32=arena.g(wname), accumulate=True, split_k=0)
-        else:
-            _lib.gemm(dz, Wm, n, K, N, **okw)                                        # dx = dz (W^T)^T, W is [K,N]
-            _lib.gemm(x, dz, K, N, n, a_mn=True, b_mn=True, out_f32=arena.g(wname), accumulate=True, split_k=0)
-        if big:
-            call("uc2_cast_f32_bf16", dx32.data_ptr(), dx.data_ptr(), dx.numel(), stream())
-        if wname.endswith("embeddings.word_embeddings.weight"):
-            arena.word_emb_dense = True          # tied decoder: the vocabulary-table gradient is dense this step
-        arena.touch(wname, *( [bname] if bname else []))
-        return dx, None, None, None, None, None, None
+        return _linear_backward(arena, wname, bname, x, dz, transposed, N, K), None, None, None, None, None, None
+
+
+def _linear_backward(arena, wname, bname, x, dz, transposed, N, K):
+    """dx of y = x W^T (+ b) given dz = dL/dy (bf16, 8-element pitch); accumulates dW and db into the arena."""
+    n = x.size(0)
+    Wm = arena.s(wname)
+    if bname:
+        call("uc2_colsum_bf16", dz.data_ptr(), dz.stride(0), n, N, arena.gp(bname), stream())
+    big = N > 8192       # vocabulary-sized contraction: split it over the SMs, accumulate in fp32
+    dx32 = torch.zeros((n, K), dtype=F32, device=x.device) if big else None
+    dx = torch.empty((n, K), dtype=BF16, device=x.device)
+    okw = dict(out_f32=dx32, accumulate=True, split_k=0) if big else dict(out_bf16=dx)
+    if not transposed:
+        _lib.gemm(dz, Wm, n, K, N, b_mn=True, **okw)                             # dx = dz W
+        _lib.gemm(dz, x, N, K, n, a_mn=True, b_mn=True, out_f32=arena.g(wname), accumulate=True, split_k=0)
+    else:
+        _lib.gemm(dz, Wm, n, K, N, **okw)                                        # dx = dz (W^T)^T, W is [K,N]
+        _lib.gemm(x, dz, K, N, n, a_mn=True, b_mn=True, out_f32=arena.g(wname), accumulate=True, split_k=0)
+    if big:
+        call("uc2_cast_f32_bf16", dx32.data_ptr(), dx.data_ptr(), dx.numel(), stream())
+    if wname.endswith("embeddings.word_embeddings.weight"):
+        arena.word_emb_dense = True          # tied decoder: the vocabulary-table gradient is dense this step
+    arena.touch(wname, *( [bname] if bname else []))
+    return dx
+
+
+class LmHeadCEFn(torch.autograd.Function):
+    """Tied MLM decoder + cross entropy as one autograd node (model/layer.py:263-264 + model/model.py:592-596):
+    logits = h W_emb^T + bias (fp32, [n, 250 002]) -> per-row CE.  Backward writes d(logits) straight as the bf16 GEMM
+    operand (uc2_ce_loss_bwd_bf16), so the 0.6 GB fp32 d(logits) tensor and its cast never exist."""
+
+    @staticmethod
+    def forward(ctx, h, arena, wname, bname, targets, ignore_index):
+        Wm = arena.s(wname)
+        n, K = h.shape
+        N = Wm.size(0)
+        h = h.contiguous()
+        logits = torch.empty((n, _pad8(N)), dtype=F32, device=h.device)
+        loss = torch.empty((n,), dtype=F32, device=h.device)
+        lse = torch.empty((n,), dtype=F32, device=h.device)
+        t = targets.to(torch.long).contiguous()
+        if n:
+            _lib.gemm(h, Wm, n, N, K, bias=arena.m(bname), out_f32=logits[:, :N])
+            call("uc2_ce_loss_fwd", logits.data_ptr(), logits.stride(0), n, N, t.data_ptr(), ignore_index,
+                 loss.data_ptr(), lse.data_ptr(), stream())
+        ctx.save_for_backward(h, logits, lse, t)
+        ctx.meta = (arena, wname, bname, N, K, ignore_index)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        arena, wname, bname, N, K, ignore_index = ctx.meta
+        h, logits, lse, t = ctx.saved_tensors
+        n = h.size(0)
+        if n == 0:
+            return torch.zeros_like(h), None, None, None, None, None
+        dloss = dloss.to(F32).contiguous()
+        dz = torch.empty((n, logits.stride(0)), dtype=BF16, device=h.device)
+        call("uc2_ce_loss_bwd_bf16", logits.data_ptr(), logits.stride(0), n, N, t.data_ptr(), ignore_index,
+             dloss.data_ptr(), lse.data_ptr(), dz.data_ptr(), dz.stride(0), stream())
+        return _linear_backward(arena, wname, bname, h, dz[:, :N], False, N, K), None, None, None, None, None
 
 
 def _pad8(n):

@@ -459,17 +459,28 @@ class _ForPretraining(UC2PreTrainedModel):
         self.vocab_pad = 0
 
     # ---- heads ----------------------------------------------------------------------------------
-    def _mlm_scores(self, rows):
+    def _mlm_transform(self, rows):
+        """dense + GELU + LayerNorm of the LM head; returns (h, decoder bias name)."""
         a = self._arena()
-        W = self._enc.prefix + "embeddings.word_embeddings.weight"
         if self.family_name == "vlxlmr":
             h = Fn.LinearFn.apply(rows, a, "cls.dense.weight", "cls.dense.bias", _lib.ACT_GELU, False, False)
             h = Fn.LayerNormFn.apply(h, a, "cls.layer_norm.weight", "cls.layer_norm.bias", float(self.config.layer_norm_eps))
-            return Fn.LinearFn.apply(h, a, W, "cls.bias", _lib.ACT_NONE, False, True)
+            return h, "cls.bias"
         t = "cls.predictions.transform."
         h = Fn.LinearFn.apply(rows, a, t + "dense.weight", t + "dense.bias", _lib.ACT_GELU, False, False)
         h = Fn.LayerNormFn.apply(h, a, t + "LayerNorm.weight", t + "LayerNorm.bias", 1e-12)
-        return Fn.LinearFn.apply(h, a, W, "cls.predictions.bias", _lib.ACT_NONE, False, True)
+        return h, "cls.predictions.bias"
+
+    def _mlm_scores(self, rows):
+        h, bias = self._mlm_transform(rows)
+        W = self._enc.prefix + "embeddings.word_embeddings.weight"
+        return Fn.LinearFn.apply(h, self._arena(), W, bias, _lib.ACT_NONE, False, True)
+
+    def _mlm_loss(self, rows, labels):
+        """Tied decoder + cross entropy fused into one node (no fp32 d(logits), see functional.LmHeadCEFn)."""
+        h, bias = self._mlm_transform(rows)
+        W = self._enc.prefix + "embeddings.word_embeddings.weight"
+        return Fn.LmHeadCEFn.apply(h, self._arena(), W, bias, labels, -100)
 
     def _feat_regress(self, rows):
         a = self._arena()
@@ -527,10 +538,9 @@ class _ForPretraining(UC2PreTrainedModel):
                         output_all_encoded_layers=False)
         mask = txt_labels != -1                       # text part only: mask columns < T (model.py:583)
         rows = Fn.MaskedRowsFn.apply(seq, mask, _count(mask, n_masked))
-        scores = self._mlm_scores(rows)
         if compute_loss:
-            return Fn.SoftmaxLossFn.apply(scores, 0, txt_labels[mask], -100)
-        return scores
+            return self._mlm_loss(rows, txt_labels[mask])
+        return self._mlm_scores(rows)
 
     def forward_mmxlm(self, input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index, img_masks,
                       txt_labels, compute_loss=True, n_masked=None):
@@ -540,10 +550,9 @@ class _ForPretraining(UC2PreTrainedModel):
                         output_all_encoded_layers=False, img_masks=img_masks)
         mask = txt_labels != -1
         rows = Fn.MaskedRowsFn.apply(seq, mask, _count(mask, n_masked))
-        scores = self._mlm_scores(rows)
         if compute_loss:
-            return Fn.SoftmaxLossFn.apply(scores, 0, txt_labels[mask], -100)
-        return scores
+            return self._mlm_loss(rows, txt_labels[mask])
+        return self._mlm_scores(rows)
 
     def forward_mmxlm_soft(self, input_ids, position_ids, img_feat, img_pos_feat, attention_mask, gather_index,
                            img_masks, tgt_masks, label_targets, compute_loss=True):
