@@ -29,8 +29,11 @@ namespace {
 constexpr int BLOCK_M = 128;   // rows per CTA; a CTA pair covers 2 x BLOCK_M
 constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+// Epilogue warps per CTA: 8 (two per TMEM lane quarter, 168 registers each), or 16 for the two ALU-heavy
+// epilogues (FFN1 + GELU with two outputs, FFN2 dgrad * gelu'): they need few registers (no fp32 operand
+// prefetch) but twice the issue slots to keep up with K = 768 mainloops.
+__host__ __device__ constexpr int epi_warps(int mode) { return (mode == 1 || mode == 2) ? 16 : 8; }
+__host__ __device__ constexpr int gemm_threads(int mode) { return 64 + 32 * epi_warps(mode); }
 constexpr int EPI_COLS = 32;   // accumulator columns per tcgen05.ld (one fp32 row slice of 128 B per thread)
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
@@ -170,7 +173,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                                               int ncol0, int ncols, uint32_t tfull, uint32_t tfull_phase,
                                               uint32_t tempty) {
     using F = Epi<MODE>;
-    constexpr int MY = BLOCK_N / 64;                 // chunks per warp: 1, 2 or 4
+    constexpr int CG = epi_warps(MODE) / 4;          // warps sharing a lane quarter; `half` = this warp's index there
+    static_assert(BLOCK_N / EPI_COLS >= CG, "tile too narrow for this many epilogue warps");
+    constexpr int MY = BLOCK_N / EPI_COLS / CG;      // chunks per warp (chunk c = CG * i + half)
     constexpr int G = MY < 2 ? MY : 2;               // chunks per group
     constexpr int W = EX == 2 ? 32 : 16;             // 32-bit words of the extra operand per chunk row
     const bool row_ok = grow < p.M;
@@ -182,8 +187,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
         if (EX != 0) {
 #pragma unroll
             for (int ii = 0; ii < G; ++ii) {
-                const int col0 = ncol0 + (2 * (g0 + ii) + half) * EPI_COLS;
-                if (p.vec_ok && col0 + EPI_COLS <= p.N && row_ok && (2 * (g0 + ii) + half) * EPI_COLS < ncols) {
+                const int col0 = ncol0 + (CG * (g0 + ii) + half) * EPI_COLS;
+                if (p.vec_ok && col0 + EPI_COLS <= p.N && row_ok && (CG * (g0 + ii) + half) * EPI_COLS < ncols) {
                     const uint8_t* src = EX == 2
                         ? reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(exb) + grow * ld_ex + col0)
                         : reinterpret_cast<const uint8_t*>(exb + grow * ld_ex + col0);
@@ -198,7 +203,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
         }
 #pragma unroll
         for (int ii = 0; ii < G; ++ii) {
-            const int c = 2 * (g0 + ii) + half;
+            const int c = CG * (g0 + ii) + half;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int col0 = ncol0 + c * EPI_COLS + h * 16;
@@ -307,7 +312,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(MODE), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_b_tail, const GemmParams p) {
     using C = Cfg<BLOCK_N, CTAS>;
@@ -339,7 +344,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull_bar(a), 1);
-            ptx::mbar_init(tempty_bar(a), EPI_WARPS * CTAS);   // one arrive per epilogue warp of every CTA
+            ptx::mbar_init(tempty_bar(a), epi_warps(MODE) * CTAS);   // one arrive per epilogue warp of every CTA
         }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -543,7 +548,7 @@ int worker_slots(cudaError_t* err) {
         if (CTAS == 2 && attr_err == cudaSuccess) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(2 * (num_sms() / 2));
-            cfg.blockDim = dim3(GEMM_THREADS);
+            cfg.blockDim = dim3(gemm_threads(MODE));
             cfg.dynamicSmemBytes = C::SMEM_BYTES;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
@@ -602,7 +607,7 @@ int launch(const uc2_gemm_args& a, const GemmParams& p_in, cudaStream_t stream) 
     const int workers = total < slots ? total : slots;
     {
         ProfScope prof(stream, 0, 2.0 * a.M * a.N * a.K);
-        launch_pdl(kern, dim3(CTAS * workers), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, CTAS, ta, tb, tb_tail, p);
+        launch_pdl(kern, dim3(CTAS * workers), dim3(gemm_threads(MODE)), C::SMEM_BYTES, stream, CTAS, ta, tb, tb_tail, p);
     }
     return check_last("gemm_bf16_kernel");
 }
