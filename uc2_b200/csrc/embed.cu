@@ -184,8 +184,14 @@ struct EmbedGrads {
     float* dy_img;      // [B*R,768] fp32, zero-initialised by the caller; accumulates d(img_linear out)
 };
 
+// Column accumulators of the backward kernel live in shared memory, one PRIVATE copy per warp, element i (0..23)
+// of lane l at slot i * 32 + l: every lane only ever touches its own slots, so the updates are plain
+// load-add-store (shared-memory atomics cost ~2 cycles per LANE; this kernel used to spend its time in them) and
+// consecutive lanes hit consecutive banks.  Slot s holds column ((s >> 5) >> 3) * 256 + (s & 31) * 8 + ((s >> 5) & 7).
+__device__ __forceinline__ int slot_col(int s) { return ((s >> 5) >> 3) * 256 + (s & 31) * 8 + ((s >> 5) & 7); }
+
 // LayerNorm backward for one row held by the warp.  in: x (pre-LN), dy.  out: dx (into dy);
-// accumulates dgamma/dbeta into shared accumulators.
+// accumulates dgamma/dbeta into this warp's accumulators.
 __device__ __forceinline__ void ln_bwd_row(const float* x, float* dy, const float* gamma, int lane, float eps,
                                            float* acc_dgamma, float* acc_dbeta) {
     float mean, rstd;
@@ -196,9 +202,8 @@ __device__ __forceinline__ void ln_bwd_row(const float* x, float* dy, const floa
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         const float xh = (x[i] - mean) * rstd;
-        const int c = col_of(lane, i >> 3) + (i & 7);
-        atomicAdd(acc_dgamma + c, dy[i] * xh);
-        atomicAdd(acc_dbeta + c, dy[i]);
+        acc_dgamma[i * 32 + lane] += dy[i] * xh;
+        acc_dbeta[i * 32 + lane] += dy[i];
         const float gd = g[i] * dy[i];
         s1 += gd;
         s2 += gd * xh;
@@ -227,15 +232,18 @@ __device__ __forceinline__ void red_row(float* dst, int lane, const float* v) {
 //  0 ln_w 1 ln_b 2 type0 | 3 fin_w 4 fin_b 5 type1 6 img_w 7 img_b 8 posln_w 9 posln_b 10 pos_b 11..17 pos_w[:,d]
 constexpr int N_ACC = 18;
 
-__global__ void __launch_bounds__(EMB_WARPS * 32)
+constexpr int EMB_BWD_WARPS = 4;      // 4 private accumulator sets x 18 x 768 fp32 = 216 KB of shared memory
+
+__global__ void __launch_bounds__(EMB_BWD_WARPS * 32)
 embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const EmbedGrads g) {
-    extern __shared__ float acc[];
-    for (int i = threadIdx.x; i < N_ACC * HID; i += blockDim.x) acc[i] = 0.f;
+    extern __shared__ float acc_all[];
+    for (int i = threadIdx.x; i < EMB_BWD_WARPS * N_ACC * HID; i += blockDim.x) acc_all[i] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    float* acc = acc_all + (threadIdx.x >> 5) * N_ACC * HID;     // this warp's private accumulators
     const long long nrows = (long long)p.B * p.S;
-    for (long long row = (long long)blockIdx.x * EMB_WARPS + (threadIdx.x >> 5); row < nrows;
-         row += (long long)gridDim.x * EMB_WARPS) {
+    for (long long row = (long long)blockIdx.x * EMB_BWD_WARPS + (threadIdx.x >> 5); row < nrows;
+         row += (long long)gridDim.x * EMB_BWD_WARPS) {
         const int b = (int)(row / p.S), j = (int)(row % p.S);
         const Src s = resolve(p, b, j);
         float dy[VPL];
@@ -252,7 +260,7 @@ embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const 
             text_presum(p, id, pos, lane, x);
             ln_bwd_row(x, dy, p.ln_w, lane, p.eps, acc + 0 * HID, acc + 1 * HID);
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) atomicAdd(acc + 2 * HID + col_of(lane, i >> 3) + (i & 7), dy[i]);
+            for (int i = 0; i < VPL; ++i) acc[2 * HID + i * 32 + lane] += dy[i];
             // nn.Embedding(padding_idx) never receives gradient on its padding row
             if (id != p.word_pad_id) red_row(g.word_emb + id * HID, lane, dy);
             if (pos != p.pos_pad_id) red_row(g.pos_emb + (long long)pos * HID, lane, dy);
@@ -276,7 +284,7 @@ embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const 
             // final LN
             ln_bwd_row(x, dy, p.fin_ln_w, lane, p.eps, acc + 3 * HID, acc + 4 * HID);
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) atomicAdd(acc + 5 * HID + col_of(lane, i >> 3) + (i & 7), dy[i]);
+            for (int i = 0; i < VPL; ++i) acc[5 * HID + i * 32 + lane] += dy[i];
             // branch: img LN
             float d1[VPL];
 #pragma unroll
@@ -287,16 +295,21 @@ embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const 
             ln_bwd_row(q, dy, p.pos_ln_w, lane, p.eps, acc + 8 * HID, acc + 9 * HID);
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
-                const int c = col_of(lane, i >> 3) + (i & 7);
-                atomicAdd(acc + 10 * HID + c, dy[i]);
+                acc[10 * HID + i * 32 + lane] += dy[i];
 #pragma unroll
-                for (int d = 0; d < 7; ++d) atomicAdd(acc + (11 + d) * HID + c, dy[i] * f7[d]);
+                for (int d = 0; d < 7; ++d) acc[(11 + d) * HID + i * 32 + lane] += dy[i] * f7[d];
             }
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < HID; c += blockDim.x) {
-        auto flush = [&](int k, float* dst) { const float v = acc[k * HID + c]; if (v != 0.f) atomicAdd(dst, v); };
+    for (int sl = threadIdx.x; sl < HID; sl += blockDim.x) {
+        const int c = slot_col(sl);
+        auto flush = [&](int k, float* dst) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < EMB_BWD_WARPS; ++w) v += acc_all[(w * N_ACC + k) * HID + sl];
+            if (v != 0.f) atomicAdd(dst, v);
+        };
         if (p.mode != 2) {
             flush(0, g.ln_w + c); flush(1, g.ln_b + c); flush(2, g.type_emb + c);
         }
@@ -435,17 +448,17 @@ extern "C" UC2_API int uc2_embed_pack_bwd(const uc2_embed_args* a, const void* d
                                  g.fin_ln_w && g.fin_ln_b && g.dy_img && g.type_emb, UC2_ERR_ARG,
                                  "embed_pack_bwd: image grads missing");
     static bool attr_set = false;
-    const int smem = N_ACC * HID * (int)sizeof(float);
+    const int smem = EMB_BWD_WARPS * N_ACC * HID * (int)sizeof(float);
     if (!attr_set) {
         UC2_CUDA(cudaFuncSetAttribute(embed_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const long long rows = (long long)p.B * p.S;
-    long long blocks = (rows + EMB_WARPS - 1) / EMB_WARPS;
-    const long long cap = 2LL * num_sms();
+    long long blocks = (rows + EMB_BWD_WARPS - 1) / EMB_BWD_WARPS;
+    const long long cap = num_sms();              // the accumulators take most of an SM's shared memory
     if (blocks > cap) blocks = cap;
-    embed_pack_bwd_kernel<<<(unsigned)blocks, EMB_WARPS * 32, smem, (cudaStream_t)stream>>>(p, (const bf16*)dout_bf16,
-                                                                                            g);
+    embed_pack_bwd_kernel<<<(unsigned)blocks, EMB_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        p, (const bf16*)dout_bf16, g);
     return check_last("embed_pack_bwd_kernel");
 }
 
