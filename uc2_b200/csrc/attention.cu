@@ -9,6 +9,7 @@
 //     while it computes dQ (phase A, warp = 16 query rows) and dK/dV (phase B, warp = 16 key rows).
 //   * S <= 512: the tiled kernels (64-row query / key tiles per CTA) kept as the general path.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace uc2 {
 namespace {
@@ -643,6 +644,151 @@ attention_bwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
     }
 }
 
+// C[16 x 64(n)] += A[16 x 16 NK] * B with ready-made A fragments; B tile rows k0.. are the k index ([k][n])
+template <int NK>
+__device__ __forceinline__ void mma_kn_a(float c[8][4], const uint32_t (*a)[4], uint32_t tile, int k0, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < NK; ++kk) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t r[4];
+            ldsm_x4_t(tile + tile_off(k0 + kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), q * 2 + (lane >> 4)), r);
+            mma16816(c[2 * q], a[kk], r[0], r[1]);
+            mma16816(c[2 * q + 1], a[kk], r[2], r[3]);
+        }
+    }
+}
+
+// Backward for S <= 160 with P and dS cached: phase A (warp = 16 query rows) computes P = softmax probabilities and
+// dS once, accumulates dQ, and parks dropout(P) and dS as bf16 [q][k] matrices in shared memory; phase B (warp = 16
+// key rows) reads them back TRANSPOSED (ldmatrix.trans) as the A operands of dV += dropout(P)^T dO and
+// dK += dS^T Q.  Five S x S x 64 products instead of the seven of the recompute kernel, and no exp / dropout hash in
+// phase B.  Shared memory: Q K V dO tiles, the two [SP][SP] bf16 matrices (row pitch SP * 2 + 16 bytes: an odd number
+// of 16-byte units keeps the transposed 8 x 8 loads bank-conflict free) and three float vectors -- a single buffer,
+// so the next head's K, V are prefetched under phase B (they are dead by then) and its Q, dO after it.
+__global__ void __launch_bounds__(BH_MAX_WARPS * 32, 1)
+attention_bwd_bh_cached_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mask,
+                               const bf16* __restrict__ dctx, const float* __restrict__ lse,
+                               const float* __restrict__ delta, bf16* __restrict__ dqkv, int B, int S, int SP,
+                               DropCfg drop) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const uint32_t sK = sQ + SP * 128, sV = sK + SP * 128, sdO = sV + SP * 128;
+    const int PST = SP * 2 + 16;
+    const uint32_t sP = sdO + SP * 128, sDS = sP + SP * PST;
+    float* s_lse = reinterpret_cast<float*>(smem + 4 * SP * 128 + 2 * SP * PST);
+    float* s_del = s_lse + SP;
+    float* s_mb = s_del + SP;
+    const int items = B * NH;
+    const int S16 = (S + 15) / 16 * 16;
+    const int t = lane & 3, g = lane >> 2;
+    auto issue_qdo = [&](int item) {
+        const int b = item / NH, h = item % NH;
+        load_tile_n(sQ, qkv, QKV_LD, (long long)b * S, h * HD, SP, S, blockDim.x);
+        load_tile_n(sdO, dctx, HID, (long long)b * S, h * HD, SP, S, blockDim.x);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto issue_kv = [&](int item) {
+        const int b = item / NH, h = item % NH;
+        load_tile_n(sK, qkv, QKV_LD, (long long)b * S, HID + h * HD, SP, S, blockDim.x);
+        load_tile_n(sV, qkv, QKV_LD, (long long)b * S, 2 * HID + h * HD, SP, S, blockDim.x);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    griddep_sync();
+    int it = blockIdx.x;
+    if (it < items) { issue_qdo(it); issue_kv(it); }
+    for (; it < items; it += gridDim.x) {
+        const int b = it / NH, h = it % NH;
+        const long long base = (long long)b * S;
+        const int nxt = it + gridDim.x;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        {
+            const float* L = lse + ((long long)b * NH + h) * S;
+            const float* Dl = delta + ((long long)b * NH + h) * S;
+            for (int i = threadIdx.x; i < SP; i += blockDim.x) {
+                s_lse[i] = i < S ? L[i] * LOG2E : INFINITY;     // +inf: padded rows contribute exp2(-inf) = 0
+                s_del[i] = i < S ? Dl[i] : 0.f;
+                s_mb[i] = i < S ? (mask[base + i] != 0 ? 0.f : MASK_LOG2) : -INFINITY;
+            }
+        }
+        __syncthreads();
+        const uint32_t hkey = drop_head_key(drop.key, b * NH + h);
+        // ---------------- phase A: P, dS (parked in shared memory) and dQ; warp = 16 query rows
+        for (int q0 = warp * 16; q0 < S; q0 += nw * 16) {
+            uint32_t qf[4][4], dof[4][4];
+            load_a_frags(sQ, q0, lane, qf);
+            load_a_frags(sdO, q0, lane, dof);
+            const float lse_lo = s_lse[q0 + g], lse_hi = s_lse[q0 + g + 8];
+            const float d_lo = s_del[q0 + g], d_hi = s_del[q0 + g + 8];
+            float dq[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+            for (int kc = 0; kc < SP; kc += KC) {
+                float sc[4][4], dp[4][4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+                    dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+                }
+                mma_nk_t<2>(sc, qf, sK, kc, lane);
+                mma_nk_t<2>(dp, dof, sV, kc, lane);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const float2 bb = *reinterpret_cast<const float2*>(s_mb + kc + n * 8 + 2 * t);
+                    float pr[4];
+                    pr[0] = ex2a(fmaf(sc[n][0], SCALE_LOG2, bb.x) - lse_lo);
+                    pr[1] = ex2a(fmaf(sc[n][1], SCALE_LOG2, bb.y) - lse_lo);
+                    pr[2] = ex2a(fmaf(sc[n][2], SCALE_LOG2, bb.x) - lse_hi);
+                    pr[3] = ex2a(fmaf(sc[n][3], SCALE_LOG2, bb.y) - lse_hi);
+                    float pd[4] = {pr[0], pr[1], pr[2], pr[3]};          // dropout(P): what dV sees
+                    if (drop.thresh) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t idx = (uint32_t)(q0 + g + (e >> 1) * 8) * (uint32_t)S + kc + n * 8 + 2 * t + (e & 1);
+                            const bool kp = drop_keep(hkey, idx, drop.thresh);
+                            pd[e] = kp ? pr[e] * drop.scale : 0.f;
+                            dp[n][e] = kp ? dp[n][e] * drop.scale : 0.f;
+                        }
+                    }
+                    sc[n][0] = pr[0] * (dp[n][0] - d_lo) * 0.125f; sc[n][1] = pr[1] * (dp[n][1] - d_lo) * 0.125f;
+                    sc[n][2] = pr[2] * (dp[n][2] - d_hi) * 0.125f; sc[n][3] = pr[3] * (dp[n][3] - d_hi) * 0.125f;
+                    const uint32_t off_lo = (q0 + g) * PST + (kc + n * 8 + 2 * t) * 2, off_hi = off_lo + 8 * PST;
+                    ptx::st_shared_b32(sP + off_lo, pack_bf16(pd[0], pd[1]));
+                    ptx::st_shared_b32(sP + off_hi, pack_bf16(pd[2], pd[3]));
+                    ptx::st_shared_b32(sDS + off_lo, pack_bf16(sc[n][0], sc[n][1]));
+                    ptx::st_shared_b32(sDS + off_hi, pack_bf16(sc[n][2], sc[n][3]));
+                }
+                mma_kn_t<2>(dq, sc, sK, kc, lane);
+            }
+            store_c_bf16(dqkv, QKV_LD, base + q0, h * HD, lane, dq, S, q0);
+        }
+        __syncthreads();                      // P and dS are complete; this head's K and V tiles are dead
+        if (nxt < items) issue_kv(nxt);
+        // ---------------- phase B: dV = dropout(P)^T dO, dK = dS^T Q; warp = 16 key rows
+        for (int k0 = warp * 16; k0 < S; k0 += nw * 16) {
+            float dk[8][4], dv[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+                dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+            }
+            const uint32_t a_off = ((lane & 7) + ((lane >> 4) << 3)) * PST + (k0 + (((lane >> 3) & 1) << 3)) * 2;
+            for (int qc = 0; qc < S16; qc += 16) {
+                uint32_t ap[1][4], ad[1][4];
+                ldsm_x4_t(sP + qc * PST + a_off, ap[0]);
+                ldsm_x4_t(sDS + qc * PST + a_off, ad[0]);
+                mma_kn_a<1>(dv, ap, sdO, qc, lane);
+                mma_kn_a<1>(dk, ad, sQ, qc, lane);
+            }
+            store_c_bf16(dqkv, QKV_LD, base + k0, HID + h * HD, lane, dk, S, k0);
+            store_c_bf16(dqkv, QKV_LD, base + k0, 2 * HID + h * HD, lane, dv, S, k0);
+        }
+        __syncthreads();                      // Q, dO, P, dS are dead
+        if (nxt < items) issue_qdo(nxt);
+    }
+}
+
 // warps per CTA for the per-head kernels: every warp gets the same number of 16-row tiles
 int bh_warps(int S) {
     const int tiles = (S + 15) / 16;
@@ -727,6 +873,15 @@ extern "C" UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long lon
     if (int rc = check_last("attention_delta_kernel")) return rc;
     if (S <= 256) {
         const int SP = (S + 31) / 32 * 32;
+        const int smem_cached = 4 * SP * 128 + 2 * SP * (SP * 2 + 16) + 3 * SP * 4;
+        if (smem_cached <= 225 * 1024) {
+            if (int rc = set_smem(attention_bwd_bh_cached_kernel, smem_cached)) return rc;
+            const int items = B * NH;
+            const int grid = items < num_sms() ? items : num_sms();
+            launch_pdl(attention_bwd_bh_cached_kernel, dim3(grid), dim3(bh_warps(S) * 32), smem_cached, s, 1,
+                       (const bf16*)qkv, attn_mask, (const bf16*)dctx, lse, delta_ws, (bf16*)dqkv, B, S, SP, drop);
+            return check_last("attention_bwd_bh_cached_kernel");
+        }
         const int nbuf = (2 * 4 * SP * 128 + 3 * SP * 4 <= 220 * 1024) ? 2 : 1;
         const int smem_bh = nbuf * 4 * SP * 128 + 3 * SP * 4;
         if (int rc = set_smem(attention_bwd_bh_kernel, smem_bh)) return rc;

@@ -121,6 +121,10 @@ __device__ __forceinline__ void stg256(void* p, uint32_t a, uint32_t b, uint32_t
                  : "memory");
 }
 
+__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
