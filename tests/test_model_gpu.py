@@ -465,3 +465,28 @@ def test_hard_negative_mining_step():
 def B_collate(items):
     from uc2_b200.batch import collate_itm_rank
     return collate_itm_rank(items, len(items))
+
+
+def test_prefetcher_order_and_contents():
+    """uc2_b200.batch.Prefetcher (the reference's PrefetchLoader, data/loader.py:75-135): every batch arrives on the
+    device unchanged and in order, nested dicts / tuples / non-tensor entries included."""
+    from uc2_b200.batch import Prefetcher
+    host = []
+    for i in range(5):
+        b = cases.batch_itm(seed=60 + i)
+        b = {k: (v.pin_memory() if torch.is_tensor(v) else ({kk: (vv.pin_memory() if torch.is_tensor(vv) else vv)
+                                                              for kk, vv in v.items()} if isinstance(v, dict) else v))
+             for k, v in b.items()}
+        host.append(("itm", b))
+    got = list(Prefetcher(iter(host), "cuda"))
+    assert len(got) == 5
+    for (t0, h), (t1, d) in zip(host, got):
+        assert t0 == t1
+        for k, v in h.items():
+            if torch.is_tensor(v):
+                assert d[k].is_cuda and torch.equal(d[k].cpu(), v)
+            elif isinstance(v, dict):
+                for kk, vv in v.items():
+                    assert torch.equal(d[k][kk].cpu(), vv) if torch.is_tensor(vv) else d[k][kk] == vv
+            else:
+                assert d[k] == v

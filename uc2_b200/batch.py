@@ -187,8 +187,13 @@ def to_device(batch, device, non_blocking=True):
 
 class Prefetcher(object):
     """data/loader.py:75-135 (PrefetchLoader): copies the NEXT batch host->device on a side stream while the
-    current step computes.  Batches must be pinned for the copy to overlap; every tensor is tied to the consuming
-    stream with record_stream (loader.py:120-134) so the caching allocator does not reuse it early."""
+    current step computes.  Batches must be pinned for the copy to overlap.
+
+    Unlike the reference, the device buffers are allocated on the COMPUTE stream (the side stream first waits for
+    whatever that stream had queued, i.e. the previous step) and only the copies run on the side stream: memory
+    allocated on one stream and consumed on another cannot be reused by the caching allocator until events
+    resolve, and with four alternating task batches that turned into a cudaMalloc -- a device-wide sync -- per
+    step, serialising the copy it was supposed to hide."""
 
     def __init__(self, loader, device):
         self.loader = loader
@@ -203,35 +208,37 @@ class Prefetcher(object):
             host = next(it)
         except StopIteration:
             return None
+        cur = torch.cuda.current_stream(self.device)
+        dst = self._alloc(host)                      # on the compute stream's pool
+        self.stream.wait_stream(cur)                 # the buffers may still be in use by already queued work
         with torch.cuda.stream(self.stream):
-            return self._move(host)
+            self._copy(dst, host)
+        return dst
 
-    def _move(self, b):
+    def _alloc(self, b):
         if torch.is_tensor(b):
-            return b.to(self.device, non_blocking=True)
+            return torch.empty(b.shape, dtype=b.dtype, device=self.device)
         if isinstance(b, dict):
-            return {k: self._move(v) for k, v in b.items()}
+            return {k: self._alloc(v) for k, v in b.items()}
         if isinstance(b, (list, tuple)):
-            return type(b)(self._move(v) for v in b)
+            return type(b)(self._alloc(v) for v in b)
         return b
 
-    def _record(self, b, stream):
-        if torch.is_tensor(b):
-            b.record_stream(stream)
-        elif isinstance(b, dict):
-            for v in b.values():
-                self._record(v, stream)
-        elif isinstance(b, (list, tuple)):
-            for v in b:
-                self._record(v, stream)
+    def _copy(self, d, h):
+        if torch.is_tensor(h):
+            d.copy_(h, non_blocking=True)
+        elif isinstance(h, dict):
+            for k in h:
+                self._copy(d[k], h[k])
+        elif isinstance(h, (list, tuple)):
+            for dv, hv in zip(d, h):
+                self._copy(dv, hv)
 
     def __iter__(self):
         it = iter(self.loader)
         nxt = self._preload(it)
         while nxt is not None:
-            cur_stream = torch.cuda.current_stream(self.device)
-            cur_stream.wait_stream(self.stream)
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)     # batch i is on the device
             batch = nxt
-            self._record(batch, cur_stream)
-            nxt = self._preload(it)
+            nxt = self._preload(it)                  # batch i+1: copied while step i computes
             yield batch
