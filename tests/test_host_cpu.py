@@ -144,12 +144,12 @@ assert torch.equal(flat2, torch.ones(10) * (r + 1))
 flat3 = torch.zeros(8 + 12 * 4 + 5)
 flat3[:8] = r + 1.0
 tab = flat3[8:8 + 48].view(12, 4)
-ids = torch.tensor([7, 1, 3 + r, 3 + r])
+ids = torch.tensor([7, 1, 3 + r, 3 + r] + [1] * r)      # ragged: rank 1 lists one more (duplicate) id than rank 0
 for i in set(ids.tolist()):
     tab[i] = (r + 1) * (i + 1)
 flat3[-5:] = 10.0 * (r + 1)
 s3 = D.GradSync(flat3, bucket_bytes=16 * 4)
-s3.sparse_rows_table(8, 12, 4, ids)
+s3.sparse_rows_table(8, 12, 4, ids, pad_row=0)                 # row 0 never carries gradient (padding_idx)
 s3.finish()                                   # the rest of the buffer goes through the dense path
 exp3 = torch.zeros(12, 4)
 exp3[1] = (1 * 2 + 2 * 2) / 2.0; exp3[7] = (1 * 8 + 2 * 8) / 2.0; exp3[3] = 1 * 4 / 2.0; exp3[4] = 2 * 5 / 2.0

@@ -32,16 +32,36 @@ def local_rank():
     return int(os.environ.get("LOCAL_RANK", 0))
 
 
+_CTL = None      # gloo group for host-side control values when the data plane is NCCL
+
+
 def init(backend=None):
     """One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*)."""
+    global _CTL
     if is_initialized() or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
         return
     backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
     if backend == "nccl":
         torch.cuda.set_device(local_rank())
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank()))
+        _CTL = dist.new_group(backend="gloo")
     else:
         dist.init_process_group(backend)
+
+
+def host_max(value):
+    """max over ranks of a host integer, exchanged on the CPU (gloo) so no GPU stream is drained for it."""
+    if size() == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.long)
+    if _CTL is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_CTL)
+    elif dist.get_backend() == "gloo":
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    else:                                   # NCCL without a control group: pay one device round trip
+        t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
 
 
 def _avg_inplace(t, async_op=False):
@@ -82,25 +102,31 @@ class GradSync(object):
         for s in range(lo, hi, self.bucket):
             self.works.append(_avg_inplace(self.flat[s:min(s + self.bucket, hi)], async_op=True))
 
-    def sparse_rows_table(self, lo, n_rows, width, row_ids):
+    def sparse_rows_table(self, lo, n_rows, width, row_ids, pad_row=0):
         """sparse_rows() for a table of exactly n_rows rows starting at flat[lo]."""
         if not self.enabled or size() == 1:
             return
         sub = GradSync.__new__(GradSync)
         sub.flat, sub.bucket, sub.works, sub.enabled, sub.done = self.flat[:lo + n_rows * width], self.bucket, [], True, []
-        sub.sparse_rows(lo, width, row_ids)
+        sub.sparse_rows(lo, width, row_ids, pad_row)
         self.done.append((lo, lo + n_rows * width))
 
-    def sparse_rows(self, lo, width, row_ids):
+    def sparse_rows(self, lo, width, row_ids, pad_row=0):
         """Exchange a row-sparse slice: flat[lo : lo + rows * width] viewed as [rows, width] whose only non-zero rows
         on this rank are `row_ids` (duplicates allowed).  Used for the word-embedding gradient when no dense term
         (the tied MLM decoder) touched it this step: ITM fine-tuning moves <= B*T rows of the 250 002 x 768 table, so
         every rank all-gathers (ids, rows) -- W x 22 MB at the bench shape -- instead of all-reducing 768 MB of zeros.
-        Static shapes, no host sync.  Result: mean over ranks, as ready()."""
+        Ranks may hold different numbers of ids (ragged batches): the lists are padded to the largest count (agreed on
+        the host through the gloo control group) with `pad_row`, a row that never carries gradient (the embedding's
+        padding_idx).  No GPU sync.  Result: mean over ranks, as ready()."""
         if not self.enabled or size() == 1:
             return
         W = size()
-        ids, _ = row_ids.reshape(-1).to(torch.long).sort()
+        ids = row_ids.reshape(-1).to(torch.long)
+        cap = host_max(ids.numel())
+        if cap > ids.numel():
+            ids = torch.cat([ids, ids.new_full((cap - ids.numel(),), int(pad_row))])
+        ids, _ = ids.sort()
         first = torch.ones_like(ids, dtype=torch.bool)
         first[1:] = ids[1:] != ids[:-1]
         n_rows = (self.flat.numel() - lo) // width

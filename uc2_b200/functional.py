@@ -226,7 +226,8 @@ def encoder_backward(enc, arena, st, dout):
                 and not getattr(arena, "word_emb_dense", False)):
             # only token rows of the vocabulary table carry gradient: exchange those rows, not 768 MB of zeros
             w_end = arena.numel[wname]
-            sync.sparse_rows_table(0, arena.shape[wname][0], arena.shape[wname][1], st.keep[0])
+            sync.sparse_rows_table(0, arena.shape[wname][0], arena.shape[wname][1], st.keep[0],
+                                   pad_row=max(int(fam.word_pad), 0))
             sync.ready(w_end, q0_off)
         else:
             sync.ready(0, q0_off)                                                        # embeddings: last
