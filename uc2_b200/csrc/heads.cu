@@ -319,7 +319,21 @@ __global__ void mse_kernel(const float* __restrict__ pred, const float* __restri
     if (loss) loss[i] = d * d;
     if (dpred) dpred[i] = 2.f * d * dloss[i];
 }
-// bf16 = gelu_erf(x) with fp32 input (+ optional derivative path):  y = gelu(x);  dx = dy * gelu'(x)
+// dz = dy * gelu'(pre), all bf16 (head transforms)
+__global__ void dgelu_bf16_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, bf16* __restrict__ out,
+                                  long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16(__bfloat162float(dy[i]) * gelu_erf_grad(__bfloat162float(pre[i])));
+}
+__global__ void f32_to_bf16_strided_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y,
+                                           long long ldy, long long rows, int cols) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    y[r * ldy + c] = __float2bfloat16(x[r * ldx + c]);
+}
+
 }  // namespace
 }  // namespace uc2
 
