@@ -199,3 +199,24 @@ def test_recall_eval_matches_reference(golden):
     img_ids = [images[i]["id"] for i in g["retrieval|img_order"]]
     log = itm_eval(torch.from_numpy(g["retrieval|scores"]), txt_ids, img_ids, txt2img, img2txts)
     np.testing.assert_allclose([log[k] for k in sorted(log)], g["retrieval|recall"], rtol=0, atol=1e-12)
+
+
+def test_dropout_hash_host_mirror():
+    """uc2_b200.dropout: the scalar and the numpy mixers agree, keys differ per site / layer / step, the keep rate
+    matches p, and thresh / scale describe the same effective probability."""
+    from uc2_b200 import dropout as DO
+    xs = np.array([0, 1, 12345, 0xFFFFFFFF, 0x9E3779B9], dtype=np.uint32)
+    assert [DO.lowbias32(int(x)) for x in xs] == [int(v) for v in DO.lowbias32_np(xs)]
+    keys = {DO.site_key(7, c, l, s) for c in (1, 2) for l in (0, 1, 11, 255) for s in range(4)}
+    assert len(keys) == 2 * 4 * 4
+    for p in (0.1, 0.25, 0.5):
+        t = DO.thresh_of(p)
+        keep = DO.keep_mask_np(DO.site_key(3, 1, 0, DO.SITE_OUT1), 1 << 20, t)
+        assert abs(keep.mean() - (1 - p)) < 2e-3
+        assert abs(DO.scale_of(p) * (1 - t / 65536.0) - 1.0) < 1e-12
+    assert DO.thresh_of(0.0) == 0 and DO.scale_of(0.0) == 1.0
+    with pytest.raises(ValueError):
+        DO.thresh_of(1.0)
+    a = DO.keep_mask_np(DO.head_key(99, 5), 4096, DO.thresh_of(0.1))
+    b = DO.keep_mask_np(DO.head_key(99, 6), 4096, DO.thresh_of(0.1))
+    assert (a != b).any()
