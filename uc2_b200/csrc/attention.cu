@@ -469,9 +469,12 @@ attention_fwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
 #pragma unroll
                 for (int n = 0; n < 4; ++n)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t idx = (uint32_t)(q0 + g + (e >> 1) * 8) * (uint32_t)S + kc + n * 8 + 2 * t + (e & 1);
-                        sc[n][e] = drop_keep(hkey, idx, drop.thresh) ? sc[n][e] * drop.scale : 0.f;
+                    for (int e = 0; e < 4; e += 2) {
+                        const uint32_t idx = (uint32_t)(q0 + g + (e >> 1) * 8) * (uint32_t)S + kc + n * 8 + 2 * t;
+                        bool k0, k1;
+                        drop_keep2(hkey, idx, drop.thresh, k0, k1);
+                        sc[n][e] = k0 ? sc[n][e] * drop.scale : 0.f;
+                        sc[n][e + 1] = k1 ? sc[n][e + 1] * drop.scale : 0.f;
                     }
             }
             mma_kn_t<2>(o, sc, sV, kc, lane);
@@ -568,9 +571,12 @@ attention_bwd_bh_kernel(const bf16* __restrict__ qkv, const long long* __restric
                     const float p3 = ex2a(fmaf(sc[n][3], SCALE_LOG2, bb.y) - lse_hi);
                     if (drop.thresh) {        // dP = dropout'(dO V^T): same mask and scale as the forward pass
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const uint32_t idx = (uint32_t)(q0 + g + (e >> 1) * 8) * (uint32_t)S + kc + n * 8 + 2 * t + (e & 1);
-                            dp[n][e] = drop_keep(hkey, idx, drop.thresh) ? dp[n][e] * drop.scale : 0.f;
+                        for (int e = 0; e < 4; e += 2) {
+                            const uint32_t idx = (uint32_t)(q0 + g + (e >> 1) * 8) * (uint32_t)S + kc + n * 8 + 2 * t;
+                            bool k0, k1;
+                            drop_keep2(hkey, idx, drop.thresh, k0, k1);
+                            dp[n][e] = k0 ? dp[n][e] * drop.scale : 0.f;
+                            dp[n][e + 1] = k1 ? dp[n][e + 1] * drop.scale : 0.f;
                         }
                     }
                     sc[n][0] = p0 * (dp[n][0] - d_lo) * 0.125f; sc[n][1] = p1 * (dp[n][1] - d_lo) * 0.125f;
@@ -744,11 +750,15 @@ attention_bwd_bh_cached_kernel(const bf16* __restrict__ qkv, const long long* __
                     float pd[4] = {pr[0], pr[1], pr[2], pr[3]};          // dropout(P): what dV sees
                     if (drop.thresh) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const uint32_t idx = (uint32_t)(q0 + g + (e >> 1) * 8) * (uint32_t)S + kc + n * 8 + 2 * t + (e & 1);
-                            const bool kp = drop_keep(hkey, idx, drop.thresh);
-                            pd[e] = kp ? pr[e] * drop.scale : 0.f;
-                            dp[n][e] = kp ? dp[n][e] * drop.scale : 0.f;
+                        for (int e = 0; e < 4; e += 2) {
+                            const uint32_t idx = (uint32_t)(q0 + g + (e >> 1) * 8) * (uint32_t)S + kc + n * 8 + 2 * t;
+                            bool kp[2];
+                            drop_keep2(hkey, idx, drop.thresh, kp[0], kp[1]);
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                pd[e + u] = kp[u] ? pr[e + u] * drop.scale : 0.f;
+                                dp[n][e + u] = kp[u] ? dp[n][e + u] * drop.scale : 0.f;
+                            }
                         }
                     }
                     sc[n][0] = pr[0] * (dp[n][0] - d_lo) * 0.125f; sc[n][1] = pr[1] * (dp[n][1] - d_lo) * 0.125f;

@@ -133,8 +133,10 @@ __device__ __forceinline__ void store8_f32(float* p, const float* f) {
     *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
-// Counter-based dropout (host mirror and rationale: uc2_b200/dropout.py).  keep <=> high 16 bits of the mixed
-// (element index ^ site key) are >= thresh = round(p * 65536); forward and backward regenerate the same mask.
+// Counter-based dropout (host mirror and rationale: uc2_b200/dropout.py).  One 32-bit mix serves TWO neighbouring
+// elements: keep(idx) <=> the (idx & 1)-th 16-bit half of lowbias32((idx >> 1) ^ site key) is >= thresh =
+// round(p * 65536); forward and backward regenerate the same mask.  Kernels that hold element pairs (2j, 2j + 1) --
+// every site does, along its fastest index -- pay one mix per pair (drop_keep2).
 struct DropCfg {
     uint32_t key;
     uint32_t thresh;     // 0: dropout off
@@ -147,7 +149,19 @@ __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
     return x;
 }
 __device__ __forceinline__ bool drop_keep(uint32_t key, uint32_t idx, uint32_t thresh) {
-    return (lowbias32(idx ^ key) >> 16) >= thresh;
+    const uint32_t h = lowbias32((idx >> 1) ^ key);
+    return ((idx & 1u) ? (h >> 16) : (h & 0xFFFFu)) >= thresh;
+}
+// keep flags of elements idx and idx + 1; one mix when idx is even (the common, aligned case)
+__device__ __forceinline__ void drop_keep2(uint32_t key, uint32_t idx, uint32_t thresh, bool& k0, bool& k1) {
+    if ((idx & 1u) == 0u) {
+        const uint32_t h = lowbias32((idx >> 1) ^ key);
+        k0 = (h & 0xFFFFu) >= thresh;
+        k1 = (h >> 16) >= thresh;
+    } else {
+        k0 = drop_keep(key, idx, thresh);
+        k1 = drop_keep(key, idx + 1u, thresh);
+    }
 }
 __host__ __device__ __forceinline__ uint32_t drop_head_key(uint32_t key, uint32_t bh) {
     return lowbias32(key ^ (bh * 0x9E3779B9u + 0x7F4A7C15u));

@@ -80,9 +80,12 @@ __device__ __forceinline__ void embed_dropout(const EmbedParams& p, int b, const
     if (p.drop.thresh == 0) return;
     const uint32_t src_row = (uint32_t)b * (uint32_t)(p.T + p.R) + (uint32_t)(s.is_img ? p.T + s.idx : s.idx);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
+    for (int i = 0; i < VPL; i += 2) {
         const uint32_t idx = src_row * HID + col_of(lane, i >> 3) + (i & 7);
-        v[i] = drop_keep(p.drop.key, idx, p.drop.thresh) ? v[i] * p.drop.scale : 0.f;
+        bool k0, k1;
+        drop_keep2(p.drop.key, idx, p.drop.thresh, k0, k1);
+        v[i] = k0 ? v[i] * p.drop.scale : 0.f;
+        v[i + 1] = k1 ? v[i + 1] * p.drop.scale : 0.f;
     }
 }
 

@@ -266,8 +266,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                     if (F::dropout(p)) {
                         const uint32_t i0 = static_cast<uint32_t>(grow) * static_cast<uint32_t>(p.N) + col0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            v[j] = drop_keep(p.drop.key, i0 + j, p.drop.thresh) ? v[j] * p.drop.scale : 0.f;
+                        for (int j = 0; j < 16; j += 2) {
+                            bool k0, k1;
+                            drop_keep2(p.drop.key, i0 + j, p.drop.thresh, k0, k1);
+                            v[j] = k0 ? v[j] * p.drop.scale : 0.f;
+                            v[j + 1] = k1 ? v[j + 1] * p.drop.scale : 0.f;
+                        }
                     }
                     if (EX == 2) {
 #pragma unroll

@@ -150,8 +150,12 @@ layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, co
             // rescaled gradient, the residual branch the plain one written above
             const uint32_t i0 = static_cast<uint32_t>(row) * HID;
 #pragma unroll
-            for (int i = 0; i < VPL; ++i)
-                d[i] = drop_keep(drop.key, i0 + col_of(lane, i >> 3) + (i & 7), drop.thresh) ? d[i] * drop.scale : 0.f;
+            for (int i = 0; i < VPL; i += 2) {
+                bool k0, k1;
+                drop_keep2(drop.key, i0 + col_of(lane, i >> 3) + (i & 7), drop.thresh, k0, k1);
+                d[i] = k0 ? d[i] * drop.scale : 0.f;
+                d[i + 1] = k1 ? d[i + 1] * drop.scale : 0.f;
+            }
 #pragma unroll
             for (int i = 0; i < 3; ++i) store8_bf16(dxm + row * HID + col_of(lane, i), d + 8 * i);
         }

@@ -5,7 +5,10 @@ model/layer.py:94 attention probabilities, 113 attention output, 154 FFN output)
 mask tensor around between forward and backward without paying HBM for it, so both passes REGENERATE the mask from
 (site key, element index):
 
-    keep(idx)  <=>  (lowbias32(idx ^ key) >> 16) >= thresh,      thresh = round(p * 65536),  scale = 1 / (1 - p)
+    keep(idx)  <=>  half(lowbias32((idx >> 1) ^ key), idx & 1) >= thresh,   thresh = round(p * 65536),  scale = 1 / (1 - p)
+
+(one 32-bit mix serves the two neighbouring elements 2j and 2j + 1: its low 16 bits decide the even one, its high 16
+bits the odd one -- every kernel holds such pairs along its fastest index and pays one mix per pair)
 
 `lowbias32` is Chris Wellons' 32-bit integer mixer (public domain); csrc/common.cuh has the same function.  The
 site key mixes the user seed, a per-forward counter, the layer and the site, so every step / layer / site draws an
@@ -68,4 +71,6 @@ def keep_mask_np(key, n, thresh, idx=None):
     if idx is None:
         idx = np.arange(n, dtype=np.uint64)
     idx = (np.asarray(idx).astype(np.uint64) & np.uint64(M32)).astype(np.uint32)
-    return (lowbias32_np(idx ^ np.uint32(key)) >> np.uint32(16)) >= np.uint32(thresh)
+    h = lowbias32_np((idx >> np.uint32(1)) ^ np.uint32(key))
+    half = np.where((idx & np.uint32(1)) == 1, h >> np.uint32(16), h & np.uint32(0xFFFF))
+    return half >= np.uint32(thresh)
