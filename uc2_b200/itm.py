@@ -58,62 +58,55 @@ class UniterForImageTextRetrieval(_ForImageTextRetrieval):
 
 
 class _HardNegMixin(object):
-    """model/itm.py:105-186: score all candidates without grad, keep the hard_size highest-scoring
-    negatives plus the positive (row 0), train on those."""
+    """In-batch hard-negative mining (the behaviour of model/itm.py:105-186).  A batch holds ONE positive pair (row 0)
+    and its candidates: one caption against many images (sample_from='t') or one image against many captions ('i').
+    In training the candidates are first scored without gradient in eval mode, the `hard_size` highest-scoring
+    negatives are kept next to the positive, and the triplet loss is taken on that reduced batch."""
+
+    _FIXED = {"t": ("input_ids",), "i": ("img_feat", "img_pos_feat")}        # the side shared by every candidate
 
     def forward(self, batch, sample_from="t", compute_loss=True):
-        batch = dict(batch)
-        batch_size = batch["attn_masks"].size(0)
-        input_ids, img_feat, img_pos_feat = batch["input_ids"], batch["img_feat"], batch["img_pos_feat"]
-        if sample_from == "t":
-            if input_ids.size(0) == 1:
-                batch["input_ids"] = input_ids.expand(batch_size, -1)
-        elif sample_from == "i":
-            if img_feat.size(0) == 1:
-                batch["img_feat"] = img_feat.expand(batch_size, -1, -1)
-            if img_pos_feat.size(0) == 1:
-                batch["img_pos_feat"] = img_pos_feat.expand(batch_size, -1, -1)
-        else:
+        if sample_from not in self._FIXED:
             raise ValueError()
-        if self.training and compute_loss:
-            with torch.no_grad():
-                self.eval()
+        batch = dict(batch)
+        n = batch["attn_masks"].size(0)
+        for key in self._FIXED[sample_from]:                 # a single shared row is broadcast over the candidates
+            if batch[key].size(0) == 1:
+                batch[key] = batch[key].expand(n, *([-1] * (batch[key].dim() - 1)))
+        if not (self.training and compute_loss):
+            return super().forward(batch, compute_loss)
+        with torch.no_grad():
+            self.eval()
+            try:
                 scores = super().forward(batch, compute_loss=False)
-                hard_batch = self._get_hard_batch(batch, scores, sample_from)
+                mined = self._get_hard_batch(batch, scores, sample_from)
+            finally:
                 self.train()
-            return super().forward(hard_batch, compute_loss=True)
-        return super().forward(batch, compute_loss)
+        return super().forward(mined, compute_loss=True)
 
     def _get_hard_batch(self, batch, scores, sample_from="t"):
-        batch = defaultdict(lambda: None, batch)
-        input_ids, position_ids = batch["input_ids"], batch["position_ids"]
-        img_feat, img_pos_feat = batch["img_feat"], batch["img_pos_feat"]
-        attention_mask, gather_index = batch["attn_masks"], batch["gather_index"]
-        hard_batch = {"sample_size": self.hard_size + 1}
-        # first example is the positive
-        hard_indices = scores.squeeze(-1)[1:].topk(self.hard_size, sorted=False)[1] + 1
-        indices = torch.cat([torch.zeros(1, dtype=torch.long, device=hard_indices.device), hard_indices])
-        attention_mask = attention_mask.index_select(0, indices)
-        gather_index = gather_index.index_select(0, indices)
-        if position_ids is not None and position_ids.size(0) != 1:
-            position_ids = position_ids[:self.hard_size + 1]
+        k = self.hard_size
+        # row 0 is the positive; the k best-scoring other rows are the hard negatives
+        keep = torch.cat([scores.new_zeros(1, dtype=torch.long),
+                          scores.reshape(-1)[1:].topk(k, sorted=False).indices + 1])
+        take = lambda t: t.index_select(0, keep)
+        head = lambda t: t[:k + 1]
+        attn, gidx = take(batch["attn_masks"]), take(batch["gather_index"])
+        pos = batch.get("position_ids")
+        if pos is not None and pos.size(0) != 1:
+            pos = head(pos)
         if sample_from == "t":
-            max_len = int(attention_mask.sum(dim=1).max().item())     # cut to minimum padding
-            max_i = max_len - input_ids.size(1)
-            attention_mask = attention_mask[:, :max_len]
-            gather_index = gather_index[:, :max_len]
-            img_feat = img_feat.index_select(0, indices)[:, :max_i, :]
-            img_pos_feat = img_pos_feat.index_select(0, indices)[:, :max_i, :]
-            input_ids = input_ids[:self.hard_size + 1]
-        elif sample_from == "i":
-            input_ids = input_ids.index_select(0, indices)
-            img_feat = img_feat[:self.hard_size + 1]
-            img_pos_feat = img_pos_feat[:self.hard_size + 1]
+            # images vary: trim the joint length to the longest kept pair (one host sync, as in the reference)
+            ids = head(batch["input_ids"])
+            longest = int(attn.sum(dim=1).max().item())
+            n_img = longest - ids.size(1)
+            attn, gidx = attn[:, :longest], gidx[:, :longest]
+            feat, box = take(batch["img_feat"])[:, :n_img], take(batch["img_pos_feat"])[:, :n_img]
         else:
-            raise ValueError()
-        hard_batch.update(input_ids=input_ids, position_ids=position_ids, img_feat=img_feat,
-                          img_pos_feat=img_pos_feat, attn_masks=attention_mask, gather_index=gather_index)
-        return hard_batch
+            ids = take(batch["input_ids"])
+            feat, box = head(batch["img_feat"]), head(batch["img_pos_feat"])
+        return {"sample_size": k + 1, "input_ids": ids, "position_ids": pos, "img_feat": feat, "img_pos_feat": box,
+                "attn_masks": attn, "gather_index": gidx}
 
 
 class UniterForImageTextRetrievalHardNeg(_HardNegMixin, UniterForImageTextRetrieval):
