@@ -321,6 +321,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
             "config": {"workload": wl_name, "model": "uc2-base 12L/768H vocab 250002 random init",
                        "per_gpu_batch": per_gpu, "seq_len": TXT + NBB, "dropout": args.dropout,
+                       "gradient_accumulation_steps": 1,
                        "l2": "working set (1.1 GB fp32 params + >5 GB activations per step) far exceeds the 126 MB L2"}}
 
     if args.impl == "reference":
@@ -445,8 +446,9 @@ def main():
     ms_step = timed(step_resident, args.steps)
     launches = (_lib.launch_count() - l0) // args.steps
     clk = clocks.summary()
-    warm = e2e_run(2)
-    for i in range(2):
+    n_warm = max(args.warmup, 3)
+    warm = e2e_run(n_warm)
+    for i in range(n_warm):
         warm(i)
     ms_e2e = timed(e2e_run(args.steps), args.steps)
 

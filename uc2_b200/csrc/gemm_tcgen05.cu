@@ -29,24 +29,33 @@ namespace {
 constexpr int BLOCK_M = 128;   // rows per CTA; a CTA pair covers 2 x BLOCK_M
 constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
+constexpr int EPI_COLS = 32;   // accumulator columns per tcgen05.ld (one fp32 row slice of 128 B per thread)
+constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
+
 // Epilogue warps per CTA: 8 (two per TMEM lane quarter, 168 registers each), or 16 for the two ALU-heavy
 // epilogues (FFN1 + GELU with two outputs, FFN2 dgrad * gelu'): they need few registers (no fp32 operand
 // prefetch) but twice the issue slots to keep up with K = 768 mainloops.
 __host__ __device__ constexpr int epi_warps(int mode) { return (mode == 1 || mode == 2) ? 16 : 8; }
 __host__ __device__ constexpr int gemm_threads(int mode) { return 64 + 32 * epi_warps(mode); }
-constexpr int EPI_COLS = 32;   // accumulator columns per tcgen05.ld (one fp32 row slice of 128 B per thread)
-constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
-template <int BLOCK_N, int CTAS>
+// fp32-output epilogues (O-proj / FFN2 forward, modes 3 and 8) leave through TMA: a warp parks its 32 x 32 fp32
+// chunk in a swizzled shared-memory box and one lane issues cp.async.bulk.tensor -- 32 rows x 128 B as one
+// request instead of 64 row-scattered 32-byte sectors through the L1 tag stage, which is what bounded those two.
+__host__ __device__ constexpr bool tma_out(int mode) { return mode == 3 || mode == 8; }
+constexpr int OUT_BOX_BYTES = 32 * 32 * 4;
+
+template <int BLOCK_N, int CTAS, int MODE = 0>
 struct Cfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_ROWS = BLOCK_N / CTAS;            // B rows (n) staged by one CTA
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - 256) / STAGE_BYTES;
+    static constexpr int STAGING_BYTES = tma_out(MODE) ? epi_warps(MODE) * OUT_BOX_BYTES : 0;
+    static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - 256 - STAGING_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;   // two accumulator buffers; 128/256/512: power of two
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+    // layout: [stages][staging boxes (1024-byte aligned: STAGE_BYTES is a multiple of 1024)][barriers]
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 256;
 };
 
 struct GemmParams {
@@ -171,7 +180,8 @@ __device__ __noinline__ void epilogue_scalar_row(const GemmParams& p, const floa
 template <int BLOCK_N, int EX, int CTAS, int MODE>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc, int lane, int half, long long grow,
                                               int ncol0, int ncols, uint32_t tfull, uint32_t tfull_phase,
-                                              uint32_t tempty) {
+                                              uint32_t tempty, const CUtensorMap* tmap_out = nullptr,
+                                              uint32_t out_box = 0) {
     using F = Epi<MODE>;
     constexpr int CG = epi_warps(MODE) / 4;          // warps sharing a lane quarter; `half` = this warp's index there
     static_assert(BLOCK_N / EPI_COLS >= CG, "tile too narrow for this many epilogue warps");
@@ -224,7 +234,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                         else ptx::mbar_arrive(tempty);
                     }
                 }
-                if (!in_tile || col0 >= p.N || !row_ok) continue;
+                if (!in_tile || col0 >= p.N) continue;
+                // the TMA-store path needs the whole warp (rows beyond M are clipped by the tensor map)
+                if (!row_ok && !tma_out(MODE)) continue;
                 const uint32_t* ex = pf + ii * W + h * (W / 2);
                 if (p.vec_ok && ncol0 + (c + 1) * EPI_COLS <= p.N) {
                     float v[16];
@@ -285,7 +297,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                         }
                     }
                     if (F::out_bf16(p)) store_bf16_row16(p.out_bf16 + grow * p.ld_out + col0, v);
-                    if (F::out_f32(p)) {
+                    if (tma_out(MODE)) {
+                        // park this row's 16 values in the swizzled box (16-byte unit u of row r sits at u ^ (r & 7))
+                        if (h == 0) {
+                            if (lane == 0) ptx::tma_store_wait_read<0>();    // the previous chunk's store has read the box
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            ptx::st_shared_v4(out_box + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4),
+                                              __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                              __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                        if (h == 1) {
+                            ptx::fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) {
+                                ptx::tma_store_2d(tmap_out, out_box, ncol0 + c * EPI_COLS,
+                                                  static_cast<int>(grow - lane));
+                                ptx::tma_store_commit();
+                            }
+                        }
+                    } else if (F::out_f32(p)) {
                         float* dst = p.out_f32 + grow * p.ld_f32 + col0;
                         if (F::accumulate(p)) {
 #pragma unroll
@@ -308,7 +340,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                     float loc[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) loc[j] = __uint_as_float(r[j]);
-                    epilogue_scalar_row(p, loc, grow, col0);
+                    if (row_ok) epilogue_scalar_row(p, loc, grow, col0);
                 }
             }
         }
@@ -318,12 +350,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
 template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_b_tail, const GemmParams p) {
-    using C = Cfg<BLOCK_N, CTAS>;
+                 const __grid_constant__ CUtensorMap tmap_b_tail, const __grid_constant__ CUtensorMap tmap_out,
+                 const GemmParams p) {
+    using C = Cfg<BLOCK_N, CTAS, MODE>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES;
     // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
@@ -331,7 +364,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::STAGES + 4);
     volatile uint32_t* tmem_ptr_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES +
+                                             8 * (2 * C::STAGES + 4));
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -342,6 +376,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
+        if (tma_out(MODE)) ptx::prefetch_tmap(&tmap_out);
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 1);
@@ -478,8 +513,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int ncols = tc.width;
             const uint32_t te = CTAS == 2 ? ptx::map_to_cta(tempty_bar(acc), 0) : tempty_bar(acc);
             if (MODE != 0)
-                epilogue_tile<BLOCK_N, Epi<MODE>::ex_kind, CTAS, MODE>(p, tacc, lane, half, grow, ncol0, ncols,
-                                                                       tfull_bar(acc), acc_phase, te);
+                epilogue_tile<BLOCK_N, Epi<MODE>::ex_kind, CTAS, MODE>(
+                    p, tacc, lane, half, grow, ncol0, ncols, tfull_bar(acc), acc_phase, te, &tmap_out,
+                    smem_base + C::STAGES * C::STAGE_BYTES + (warp_idx - 2) * OUT_BOX_BYTES);
             else if (ex_kind == 0)
                 epilogue_tile<BLOCK_N, 0, CTAS, 0>(p, tacc, lane, half, grow, ncol0, ncols, tfull_bar(acc), acc_phase, te);
             else if (ex_kind == 1)
@@ -488,6 +524,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 epilogue_tile<BLOCK_N, 2, CTAS, 0>(p, tacc, lane, half, grow, ncol0, ncols, tfull_bar(acc), acc_phase, te);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (tma_out(MODE) && lane == 0) ptx::tma_store_wait_all<0>();    // shared memory must outlive the stores
     }
 
     // ------------------------------------------- teardown -------------------------------------------
@@ -538,10 +575,26 @@ int make_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, 
     return UC2_OK;
 }
 
+// fp32 output [rows][cols], row pitch ld elements; box = 32 rows x 32 columns (128 B), SWIZZLE_128B
+int make_tmap_out_f32(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld) {
+    EncodeTiledFn enc = get_encode_fn();
+    UC2_REQUIRE(enc != nullptr, UC2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UC2_REQUIRE(r == CUDA_SUCCESS, UC2_ERR_CUDA, "cuTensorMapEncodeTiled(out f32) failed (%d): rows=%lld cols=%lld ld=%lld",
+                (int)r, rows, cols, ld);
+    return UC2_OK;
+}
+
 // How many persistent workers (CTAs, or CTA pairs) the device can hold for one kernel instantiation.
 template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS, int MODE>
 int worker_slots(cudaError_t* err) {
-    using C = Cfg<BLOCK_N, CTAS>;
+    using C = Cfg<BLOCK_N, CTAS, MODE>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     static int slots = 0;
@@ -569,7 +622,7 @@ int worker_slots(cudaError_t* err) {
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS, int MODE = 0>
 int launch(const uc2_gemm_args& a, const GemmParams& p_in, cudaStream_t stream) {
-    using C = Cfg<BLOCK_N, CTAS>;
+    using C = Cfg<BLOCK_N, CTAS, MODE>;
     static_assert(C::STAGES >= 3, "pipeline too shallow");
     static_assert(CTAS == 1 || C::B_ROWS % 64 == 0, "a CTA pair needs BLOCK_N >= 128");
     auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, CTAS, MODE>;
@@ -587,6 +640,11 @@ int launch(const uc2_gemm_args& a, const GemmParams& p_in, cudaStream_t stream) 
     if (rc) return rc;
     GemmParams p = p_in;
     CUtensorMap tb_tail = tb;
+    CUtensorMap tout = tb;                    // only read by the TMA-store modes
+    if (tma_out(MODE)) {
+        rc = make_tmap_out_f32(&tout, a.out_f32, a.M, a.N, a.ld_f32);
+        if (rc) return rc;
+    }
     const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
     p.tail_start = tiles_mn;
     p.tail_split = 1;
@@ -611,7 +669,7 @@ int launch(const uc2_gemm_args& a, const GemmParams& p_in, cudaStream_t stream) 
     const int workers = total < slots ? total : slots;
     {
         ProfScope prof(stream, 0, 2.0 * a.M * a.N * a.K);
-        launch_pdl(kern, dim3(CTAS * workers), dim3(gemm_threads(MODE)), C::SMEM_BYTES, stream, CTAS, ta, tb, tb_tail, p);
+        launch_pdl(kern, dim3(CTAS * workers), dim3(gemm_threads(MODE)), C::SMEM_BYTES, stream, CTAS, ta, tb, tb_tail, tout, p);
     }
     return check_last("gemm_bf16_kernel");
 }
