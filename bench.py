@@ -99,16 +99,41 @@ def nbytes(batch):
 # clocks sampler (nvidia-smi during the timed region)
 # --------------------------------------------------------------------------------------------------
 class Clocks(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs: NVML every 20 ms when the
+    bindings are importable (nvidia-ml-py), else `nvidia-smi --query-gpu` every ~100 ms."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    n = self.nvml
+                    mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    try:
+                        mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    self.samples.append([str(mhz), str(self.max_mhz)] +
+                                        ["Active" if mask & bit else "Not Active" for _, bit in self.BITS])
+                    time.sleep(0.02)
+                    continue
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in o.strip().split(",")]
@@ -124,10 +149,11 @@ class Clocks(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        names = [n for n, _ in self.BITS]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -300,8 +326,8 @@ def run_retrieval(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="itm", choices=["itm", "pretrain", "retrieval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
