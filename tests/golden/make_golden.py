@@ -279,7 +279,40 @@ def case_retrieval():
     return out
 
 
+def case_loader():
+    """data/sampler.py TokenBucketSampler and data/loader.py MetaLoader driven by the seeded `random` module."""
+    import random
+    out = {}
+    lens = [int(x) for x in cases.synth.det_randint(700, 18, 161, 5, 1)]
+    out["lens"] = np.array(lens)
+    for k, (bucket, budget, drop) in enumerate([(256, 2560, False), (128, 10240, True), (512, 1920, False)]):
+        random.seed(100 + k)
+        batches = [b for b in iter(R.sampler.TokenBucketSampler(lens, bucket, budget, droplast=drop))]
+        out[f"sampler{k}|cfg"] = np.array([bucket, budget, int(drop)])
+        out[f"sampler{k}|sizes"] = np.array([len(b) for b in batches])
+        out[f"sampler{k}|flat"] = np.array([i for b in batches for i in b])
+
+    class Loader(torch.utils.data.DataLoader):      # MetaLoader insists on DataLoader instances
+        def __init__(self, items):
+            self.items = items
+
+        def __iter__(self):
+            return iter(self.items)
+    random.seed(7)
+    ml = R.loader.MetaLoader({"mlm": (Loader([1, 2, 3]), 2), "itm": Loader([10, 20]), "mrfr": (Loader([5]), 1)},
+                             accum_steps=3, distributed=False)
+    seq = []
+    for i, (task, batch) in enumerate(ml):
+        seq.append((task, batch))
+        if i == 59:
+            break
+    out["meta|tasks"] = np.array([t for t, _ in seq])
+    out["meta|batches"] = np.array([b for _, b in seq])
+    return out
+
+
 CASES = {
+    "loader": case_loader,
     "retrieval": case_retrieval,
     "pretrain": lambda: case_pretrain("vlxlmr"),
     "pretrain_uniter": lambda: case_pretrain("uniter"),

@@ -35,7 +35,10 @@ def install(valid_token_ids=None):
     _mod("msgpack_numpy", patch=lambda: None)
     tz = _mod("toolz")
     tz.sandbox = _mod("toolz.sandbox", unzip=lambda s: zip(*s))
-    _mod("cytoolz", concat=itertools.chain.from_iterable, partition_all=None, curry=lambda f: f)
+    def partition_all(n, seq):
+        seq = list(seq)
+        return [tuple(seq[i:i + n]) for i in range(0, len(seq), n)]
+    _mod("cytoolz", concat=itertools.chain.from_iterable, partition_all=partition_all, curry=lambda f: f)
     _mod("tensorboardX", SummaryWriter=object)
     # (2) const_variable downloads xlm-roberta-base at import; only the unused vis_cls head needs it
     pkg = types.ModuleType("model")
@@ -50,6 +53,11 @@ def install(valid_token_ids=None):
     opk = types.ModuleType("optim")
     opk.__path__ = [REF + "/optim"]
     sys.modules["optim"] = opk
+    # data/loader.py imports utils.distributed (horovod helpers): register the package so it resolves from the
+    # reference tree without executing anything else of utils/
+    upk = types.ModuleType("utils")
+    upk.__path__ = [REF + "/utils"]
+    sys.modules["utils"] = upk
     import model.ot as ot
     # (4) ot.trace builds a uint8 eye for masked_select, which torch>=2 rejects; same maths:
     ot.trace = lambda x: x.diagonal(dim1=-2, dim2=-1).sum(-1)
@@ -67,9 +75,11 @@ def load():
     import data.data as dd
     import data.itm as di
     import data.mrm as dm
+    import data.sampler as dsamp
+    import data.loader as dload
     import importlib.util
     spec = importlib.util.spec_from_file_location("ref_eval_itm", REF + "/eval/itm.py")
     ev = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ev)
     return types.SimpleNamespace(model=mm, itm=mi, ot=mo, layer=ml, adamw=oa, misc=om, sched=osch,
-                                 data=dd, data_itm=di, data_mrm=dm, eval_itm=ev)
+                                 data=dd, data_itm=di, data_mrm=dm, eval_itm=ev, sampler=dsamp, loader=dload)

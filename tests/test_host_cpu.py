@@ -220,3 +220,38 @@ def test_dropout_hash_host_mirror():
     a = DO.keep_mask_np(DO.head_key(99, 5), 4096, DO.thresh_of(0.1))
     b = DO.keep_mask_np(DO.head_key(99, 6), 4096, DO.thresh_of(0.1))
     assert (a != b).any()
+
+
+def test_token_bucket_sampler_and_meta_loader_match_reference(golden):
+    """uc2_b200.loader against batches / task sequences produced by the reference's data/sampler.py and
+    data/loader.py under the same `random` seeds (tests/golden/loader.npz): index lists bit-exact."""
+    import random
+    from uc2_b200.loader import MetaLoader, TokenBucketSampler
+    g = golden("loader")
+    lens = [int(x) for x in g["lens"]]
+    for k in range(3):
+        bucket, budget, drop = (int(x) for x in g[f"sampler{k}|cfg"])
+        random.seed(100 + k)
+        batches = [b for b in iter(TokenBucketSampler(lens, bucket, budget, droplast=bool(drop)))]
+        assert [len(b) for b in batches] == list(g[f"sampler{k}|sizes"])
+        assert [i for b in batches for i in b] == list(g[f"sampler{k}|flat"])
+        for b in batches:                      # the token budget holds and full batches are multiples of 8
+            assert max(lens[i] for i in b) * len(b) <= budget
+        if drop:
+            assert all(len(b) % 8 == 0 for b in batches)
+    random.seed(7)
+    ml = MetaLoader({"mlm": ([1, 2, 3], 2), "itm": [10, 20], "mrfr": ([5], 1)}, accum_steps=3, distributed=False)
+    seq = []
+    for i, tb in enumerate(ml):
+        seq.append(tb)
+        if i == 59:
+            break
+    assert [t for t, _ in seq] == list(g["meta|tasks"])
+    assert [b for _, b in seq] == list(g["meta|batches"])
+    # distributed mode: every rank draws the same task sequence from its own identically seeded stream
+    a = MetaLoader({"x": ([1], 3), "y": [2]}, accum_steps=2, distributed=True, task_seed=11)
+    b = MetaLoader({"x": ([1], 3), "y": [2]}, accum_steps=2, distributed=True, task_seed=11)
+    ia, ib = iter(a), iter(b)
+    assert [next(ia)[0] for _ in range(40)] == [next(ib)[0] for _ in range(40)]
+    with pytest.raises(ValueError):
+        len(TokenBucketSampler(lens, 8, 100))
