@@ -1,6 +1,8 @@
 """GPU: fused multi-tensor AdamW + clip + zero_grad + shadow refresh against the oracle restatement of
 optim/adamw.py (itself pinned to the reference's AdamW by tests/golden/adamw.npz), and a short training
 run against the oracle training loop."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -114,3 +116,68 @@ def test_training_steps_follow_oracle():
                 O.adamw_step(ref[k], ref[k].grad, rm[k], rv[k], s, lr, 0.9, 0.98, 1e-6, 0.0 if O.no_decay(k) else wd)
     np.testing.assert_allclose(got_losses, ref_losses, rtol=2e-3)
     assert ref_losses[2] < ref_losses[0]        # and it actually trains
+
+
+def test_checkpoint_resume_is_exact(tmp_path):
+    """Train 2 steps, save with the reference's checkpoint layout (utils/save.py), restore into a FRESH model and
+    optimizer, train 2 more: parameters equal an uninterrupted 4-step run (dropout off; the only run-to-run
+    difference is the order of fp32 atomics in the wgrad / embedding-gradient accumulation)."""
+    from uc2_b200 import model
+    from uc2_b200.batch import to_device
+    from uc2_b200.optim import AdamW
+    from uc2_b200.save import ModelSaver, TrainingRestorer
+    from uc2_b200.train import TrainStep
+    from uc2_b200.utils import set_dropout
+    from oracle import uc2_oracle as O
+    cfg = cases.config(2)
+    sd = cases.weights(cfg, "pretrain")
+    bd = to_device(cases.batch_mrfr(seed=31), "cuda")
+
+    def fresh():
+        m = model.VLXLMRForPretraining(cfg, 2048, 1601)
+        m.load_state_dict(cases.with_aliases(sd, "pretrain"), strict=False)
+        m.cuda().train()
+        set_dropout(m, 0)
+        decay = [p for n, p in m.named_parameters() if not O.no_decay(n)]
+        nodecay = [p for n, p in m.named_parameters() if O.no_decay(n)]
+        opt = AdamW([{"params": decay, "weight_decay": 0.01}, {"params": nodecay, "weight_decay": 0.0}], lr=2e-4,
+                    betas=(0.9, 0.98))
+        return m, opt, TrainStep(m, opt, grad_norm=5.0)
+
+    m1, o1, s1 = fresh()
+    for _ in range(4):
+        s1(bd, "mrfr")
+    m2, o2, s2 = fresh()
+    r2 = TrainingRestorer(str(tmp_path), m2, o2, save_steps=2)
+    for _ in range(2):
+        s2(bd, "mrfr")
+        r2.step()
+    ModelSaver(str(tmp_path)).save(m2, 2, o2)
+    osd = o2.state_dict()
+    assert set(osd) == {"state", "param_groups"} and osd["param_groups"][0]["params"][0] == 0
+    n_with_grad = sum(1 for p in m2.parameters() if float(p.grad.abs().sum()) >= 0 and True)
+    assert all(st["step"] == 2 for st in osd["state"].values()) and 0 < len(osd["state"]) <= n_with_grad
+    assert os.path.exists(tmp_path / "restore.pt") and os.path.exists(tmp_path / "model_step_2.pt")
+    assert os.path.exists(tmp_path / "train_state_2.pt")
+    m3, o3, s3 = fresh()
+    r3 = TrainingRestorer(str(tmp_path), m3, o3, save_steps=2)
+    assert r3.global_step == 2 and o3.global_step == 2
+    for _ in range(2):
+        s3(bd, "mrfr")
+    p1, p3 = dict(m1.named_parameters()), dict(m3.named_parameters())
+    # Adam divides by sqrt(v): on elements whose gradient is at the fp32-atomics noise floor the update direction is
+    # noise too, so two runs may differ there by up to lr = 2e-4 per step.  A resume bug (lost moments, wrong step
+    # count, stale shadows) would move EVERY element by that much; here almost none may move.
+    worst = []
+    for n in p1:
+        a, b = p3[n].detach().cpu().numpy(), p1[n].detach().cpu().numpy()
+        d = np.abs(a - b)
+        worst.append((float(d.max()), float((d > 1e-5).mean()), n))
+        assert d.max() <= 4 * 2e-4, (n, float(d.max()))
+    frac = max(w[1] for w in worst)
+    assert frac < 0.02, sorted(worst, reverse=True)[:5]
+    # and the restored run really continued from step 2 (a restart from scratch would sit far away)
+    p0 = cases.weights(cfg, "pretrain")
+    moved = float((p1["roberta.encoder.layer.0.output.dense.weight"].detach().cpu()
+                   - p0["roberta.encoder.layer.0.output.dense.weight"]).abs().mean())
+    assert moved > 1e-4

@@ -145,10 +145,64 @@ class AdamW(object):
         if not self._fused_zero and self._arena is not None:
             self._arena.zero_grad()
 
+    # ---------------------------------------------------------------------------------------------
+    # checkpoint format: torch.optim.Optimizer.state_dict() layout, i.e. what the reference's ModelSaver /
+    # TrainingRestorer write and read (utils/save.py:58-80, 164-213): {'state': {param index: {'step', 'exp_avg',
+    # 'exp_avg_sq'}}, 'param_groups': [{..., 'params': [indices]}]}.  Parameters that never had a gradient have no
+    # state entry (optim/adamw.py:52-53 skips them).
+    def _param_order(self):
+        return [p for g in self.param_groups for p in g["params"]]
+
     def state_dict(self):
-        return {"global_step": self.global_step, "act": list(getattr(self, "_act_host", [])),
-                "exp_avg": getattr(self, "exp_avg", None), "exp_avg_sq": getattr(self, "exp_avg_sq", None),
-                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+        groups, k = [], 0
+        for g in self.param_groups:
+            d = {key: v for key, v in g.items() if key != "params"}
+            d["params"] = list(range(k, k + len(g["params"])))
+            k += len(g["params"])
+            groups.append(d)
+        state = {}
+        if self._arena is not None:
+            a = self._arena
+            by_ptr = {a.params[n].data_ptr(): n for n in a.names}
+            for i, p in enumerate(self._param_order()):
+                n = by_ptr[p.data_ptr()]
+                act = self._act_host[a.index[n]]
+                if act < 0:
+                    continue
+                o, num = a.offset[n], a.numel[n]
+                state[i] = {"step": self.global_step - act + 1,
+                            "exp_avg": self.exp_avg[o:o + num].view(a.shape[n]).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + num].view(a.shape[n]).clone()}
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        """Accepts the layout above (from this class or from the reference's optim/adamw.py via torch.optim)."""
+        self._bind()
+        a = self._arena
+        if len(sd["param_groups"]) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            if len(saved["params"]) != len(g["params"]):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of "
+                                 "optimizer's group")
+            for key, v in saved.items():
+                if key != "params":
+                    g[key] = tuple(v) if key == "betas" else v
+        by_ptr = {a.params[n].data_ptr(): n for n in a.names}
+        order = self._param_order()
+        steps = [int(st["step"]) for st in sd["state"].values()]
+        self.global_step = max(steps) if steps else 0
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self._act_host = [-1] * len(a.names)
+        for i, st in sd["state"].items():
+            n = by_ptr[order[int(i)].data_ptr()]
+            o, num = a.offset[n], a.numel[n]
+            self.exp_avg[o:o + num].copy_(st["exp_avg"].reshape(-1).to(self.exp_avg.device, torch.float32))
+            self.exp_avg_sq[o:o + num].copy_(st["exp_avg_sq"].reshape(-1).to(self.exp_avg.device, torch.float32))
+            self._act_host[a.index[n]] = self.global_step - int(st["step"]) + 1
+            a.active[n] = True
+        self._act.copy_(torch.tensor(self._act_host, dtype=torch.int32))
 
 
 def clip_grad_norm_(optimizer, max_norm):
