@@ -59,12 +59,19 @@ layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma
     }
 }
 
-// Backward.  Each warp walks rows with a grid stride and keeps dgamma/dbeta/dbias partial sums in registers
-// (72 accumulators + the row itself: ~150 registers, so only 8 warps fit on an SM).  Memory-level parallelism
-// therefore comes from a per-warp ring of LN_STAGES rows in shared memory filled by 1-D bulk copies
-// (cp.async.bulk, completion on an mbarrier per slot): 8 warps x 4 rows x 4.5 KB = 147 KB in flight per SM,
-// which is what it takes to keep HBM busy (the register-only version reached 1.9 TB/s).
+// Backward.  TWO warps share a row (384 columns = 12 values per lane each) and walk rows with a grid stride,
+// keeping their halves of the dgamma/dbeta/dbias partial sums in registers (36 accumulators + the half row: under
+// 128 registers, so 16 warps fit on an SM; the one-warp-per-row version needed ~150 and was instruction-latency
+// bound with 8).  The row statistics and the two projections are combined across the pair through shared memory
+// and a 64-thread named barrier.  Memory-level parallelism comes from a per-pair ring of LN_STAGES rows in shared
+// memory filled by 1-D bulk copies (cp.async.bulk, completion on an mbarrier per slot): 8 pairs x 4 rows x 4.5 KB
+// = 147 KB in flight per SM, which is what it takes to keep HBM busy (the register-only version reached 1.9 TB/s).
 constexpr int LN_STAGES = 4;
+constexpr int LNB_PAIRS = 8;
+constexpr int LNB_WARPS = 2 * LNB_PAIRS;
+constexpr int HV = 12;                                 // values per lane of one half row
+
+__device__ __forceinline__ int col_h(int half, int lane, int j) { return half * (HID / 2) + j * 128 + lane * 4; }
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -72,8 +79,24 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  : "memory");
 }
 
+__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+__device__ __forceinline__ void load4_bf16(const bf16* p, float* f) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+
+__device__ __forceinline__ void store4_bf16(bf16* p, const float* f) {
+    uint2 u;
+    *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(f[0], f[1]);
+    *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
 template <bool F32>
-__global__ void __launch_bounds__(LN_WARPS * 32, 1)
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
 layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ gamma,
                      float eps, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dbias, long long rows, bf16* __restrict__ dxm, DropCfg drop) {
@@ -81,57 +104,77 @@ layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, co
     constexpr int SLOT = XB + HID * 2;                // x row + dy row
     extern __shared__ __align__(128) uint8_t ln_smem[];
     __shared__ float red[3 * HID];
-    __shared__ __align__(8) unsigned long long bars[LN_WARPS * LN_STAGES];
+    __shared__ float2 part_a[LNB_PAIRS][2], part_b[LNB_PAIRS][2];
+    __shared__ __align__(8) unsigned long long bars[LNB_PAIRS * LN_STAGES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp >> 1, half = warp & 1;
     for (int i = threadIdx.x; i < 3 * HID; i += blockDim.x) red[i] = 0.f;
-    const uint32_t ring = ptx::smem_u32(ln_smem) + warp * LN_STAGES * SLOT;
-    const uint32_t bar0 = ptx::smem_u32(bars) + warp * LN_STAGES * 8;
-    if (lane == 0) {
+    const uint32_t ring = ptx::smem_u32(ln_smem) + pair * LN_STAGES * SLOT;
+    const uint32_t bar0 = ptx::smem_u32(bars) + pair * LN_STAGES * 8;
+    const bool loader = half == 0 && lane == 0;
+    if (loader) {
         for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
     __syncthreads();
     griddep_sync();
-    const long long stride = (long long)gridDim.x * LN_WARPS;
-    const long long first = (long long)blockIdx.x * LN_WARPS + warp;
-    auto issue = [&](long long row, int s) {      // lane 0 only
+    const long long stride = (long long)gridDim.x * LNB_PAIRS;
+    const long long first = (long long)blockIdx.x * LNB_PAIRS + pair;
+    auto issue = [&](long long row, int s) {      // loader lane only
         ptx::mbar_arrive_expect_tx(bar0 + 8 * s, SLOT);
         bulk_load(ring + s * SLOT, static_cast<const uint8_t*>(x) + row * XB, XB, bar0 + 8 * s);
         bulk_load(ring + s * SLOT + XB, dy + row * HID, HID * 2, bar0 + 8 * s);
     };
-    if (lane == 0)
+    if (loader)
         for (int s = 0; s < LN_STAGES; ++s)
             if (first + s * stride < rows) issue(first + s * stride, s);
-    float g[VPL];
+    float g[HV];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) load8_f32(gamma + col_of(lane, i), g + 8 * i);
-    float ag[VPL], ab[VPL], ax[VPL];
+    for (int j = 0; j < 3; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(gamma + col_h(half, lane, j));
+        g[4 * j] = t.x; g[4 * j + 1] = t.y; g[4 * j + 2] = t.z; g[4 * j + 3] = t.w;
+    }
+    float ag[HV], ab[HV], ax[HV];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) ag[i] = ab[i] = ax[i] = 0.f;
+    for (int i = 0; i < HV; ++i) ag[i] = ab[i] = ax[i] = 0.f;
     int s = 0;
     uint32_t phase = 0;
     for (long long row = first; row < rows; row += stride) {
         ptx::mbar_wait(bar0 + 8 * s, phase);
-        float v[VPL], d[VPL];
-        const uint8_t* slot = ln_smem + (warp * LN_STAGES + s) * SLOT;
+        float v[HV], d[HV];
+        const uint8_t* slot = ln_smem + (pair * LN_STAGES + s) * SLOT;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            if (F32) load8_f32(reinterpret_cast<const float*>(slot) + col_of(lane, i), v + 8 * i);
-            else     load8_bf16(reinterpret_cast<const bf16*>(slot) + col_of(lane, i), v + 8 * i);
-            load8_bf16(reinterpret_cast<const bf16*>(slot + XB) + col_of(lane, i), d + 8 * i);
+        for (int j = 0; j < 3; ++j) {
+            const int c = col_h(half, lane, j);
+            if (F32) {
+                const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(slot) + c);
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            } else {
+                load4_bf16(reinterpret_cast<const bf16*>(slot) + c, v + 4 * j);
+            }
+            load4_bf16(reinterpret_cast<const bf16*>(slot + XB) + c, d + 4 * j);
         }
-        __syncwarp();                                  // every lane has its copy: the slot can be refilled
-        if (lane == 0 && row + LN_STAGES * stride < rows) {
+        // row statistics: sum and sum of squares over this half, combined with the other half's
+        float sx = 0.f, sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < HV; ++i) { sx += v[i]; sq += v[i] * v[i]; }
+        sx = warp_sum(sx);
+        sq = warp_sum(sq);
+        if (lane == 0) part_a[pair][half] = make_float2(sx, sq);
+        pair_sync(pair);                               // also: both warps hold their copy, the slot can be refilled
+        if (loader && row + LN_STAGES * stride < rows) {
             ptx::fence_proxy_async();
             issue(row + LN_STAGES * stride, s);
         }
         if (++s == LN_STAGES) { s = 0; phase ^= 1u; }
-        float mean, rstd;
-        stats(v, eps, mean, rstd);
+        const float2 pa0 = part_a[pair][0], pa1 = part_a[pair][1];
+        const float mean = (pa0.x + pa1.x) * (1.0f / HID);
+        const float var = fmaxf((pa0.y + pa1.y) * (1.0f / HID) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
+        for (int i = 0; i < HV; ++i) {
             v[i] = (v[i] - mean) * rstd;          // xhat
             ag[i] += d[i] * v[i];
             ab[i] += d[i];
@@ -139,32 +182,37 @@ layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, co
             s1 += d[i];
             s2 += d[i] * v[i];
         }
-        s1 = warp_sum(s1) * (1.0f / HID);
-        s2 = warp_sum(s2) * (1.0f / HID);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) part_b[pair][half] = make_float2(s1, s2);
+        pair_sync(pair);
+        const float2 pb0 = part_b[pair][0], pb1 = part_b[pair][1];
+        s1 = (pb0.x + pb1.x) * (1.0f / HID);
+        s2 = (pb0.y + pb1.y) * (1.0f / HID);
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) d[i] = rstd * (d[i] - s1 - v[i] * s2);
+        for (int i = 0; i < HV; ++i) d[i] = rstd * (d[i] - s1 - v[i] * s2);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) store8_bf16(dx + row * HID + col_of(lane, i), d + 8 * i);
+        for (int j = 0; j < 3; ++j) store4_bf16(dx + row * HID + col_h(half, lane, j), d + 4 * j);
         if (dxm) {
             // x was dropout(dense) + residual: the dense branch (its wgrad / dgrad / bias gradient) sees the masked,
             // rescaled gradient, the residual branch the plain one written above
             const uint32_t i0 = static_cast<uint32_t>(row) * HID;
 #pragma unroll
-            for (int i = 0; i < VPL; i += 2) {
+            for (int i = 0; i < HV; i += 2) {
                 bool k0, k1;
-                drop_keep2(drop.key, i0 + col_of(lane, i >> 3) + (i & 7), drop.thresh, k0, k1);
+                drop_keep2(drop.key, i0 + col_h(half, lane, i >> 2) + (i & 3), drop.thresh, k0, k1);
                 d[i] = k0 ? d[i] * drop.scale : 0.f;
                 d[i + 1] = k1 ? d[i + 1] * drop.scale : 0.f;
             }
 #pragma unroll
-            for (int i = 0; i < 3; ++i) store8_bf16(dxm + row * HID + col_of(lane, i), d + 8 * i);
+            for (int j = 0; j < 3; ++j) store4_bf16(dxm + row * HID + col_h(half, lane, j), d + 4 * j);
         }
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) ax[i] += d[i];
+        for (int i = 0; i < HV; ++i) ax[i] += d[i];
     }
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int c = col_of(lane, i >> 3) + (i & 7);
+    for (int i = 0; i < HV; ++i) {
+        const int c = col_h(half, lane, i >> 2) + (i & 3);
         atomicAdd(red + c, ag[i]);
         atomicAdd(red + HID + c, ab[i]);
         atomicAdd(red + 2 * HID + c, ax[i]);
@@ -249,17 +297,17 @@ extern "C" UC2_API int uc2_layernorm_bwd_dropout(const void* x, int x_is_f32, co
     UC2_REQUIRE(x && dy && gamma && dx && dgamma && dbeta && rows > 0, UC2_ERR_ARG, "layernorm_bwd: bad args");
     UC2_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma), UC2_ERR_ARG,
                 "layernorm_bwd: pointers must be 16-byte aligned");
-    long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+    long long blocks = (rows + LNB_PAIRS - 1) / LNB_PAIRS;
     const long long cap = num_sms();                  // one CTA per SM: the row ring takes most of its shared memory
     if (blocks > cap) blocks = cap;
-    const int smem = LN_WARPS * LN_STAGES * ((x_is_f32 ? HID * 4 : HID * 2) + HID * 2);
+    const int smem = LNB_PAIRS * LN_STAGES * ((x_is_f32 ? HID * 4 : HID * 2) + HID * 2);
     if (x_is_f32) {
         UC2_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        launch_pdl(layernorm_bwd_kernel<true>, dim3((unsigned)blocks), dim3(LN_WARPS * 32), smem, (cudaStream_t)stream, 1,
+        launch_pdl(layernorm_bwd_kernel<true>, dim3((unsigned)blocks), dim3(LNB_WARPS * 32), smem, (cudaStream_t)stream, 1,
                    x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows, (bf16*)dx_masked, drop);
     } else {
         UC2_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        launch_pdl(layernorm_bwd_kernel<false>, dim3((unsigned)blocks), dim3(LN_WARPS * 32), smem, (cudaStream_t)stream, 1,
+        launch_pdl(layernorm_bwd_kernel<false>, dim3((unsigned)blocks), dim3(LNB_WARPS * 32), smem, (cudaStream_t)stream, 1,
                    x, (const bf16*)dy, gamma, eps, (bf16*)dx, dgamma, dbeta, dbias, rows, (bf16*)dx_masked, drop);
     }
     return check_last("layernorm_bwd_kernel");
