@@ -675,15 +675,15 @@ __device__ __forceinline__ void mma_kn_a(float c[8][4], const uint32_t (*a)[4], 
 __global__ void __launch_bounds__(BH_MAX_WARPS * 32, 1)
 attention_bwd_bh_cached_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mask,
                                const bf16* __restrict__ dctx, const float* __restrict__ lse,
-                               const float* __restrict__ delta, bf16* __restrict__ dqkv, int B, int S, int SP,
+                               const bf16* __restrict__ ctx, bf16* __restrict__ dqkv, int B, int S, int SP,
                                DropCfg drop) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
     const uint32_t sK = sQ + SP * 128, sV = sK + SP * 128, sdO = sV + SP * 128;
     const int PST = SP * 2 + 16;
-    const uint32_t sP = sdO + SP * 128, sDS = sP + SP * PST;
-    float* s_lse = reinterpret_cast<float*>(smem + 4 * SP * 128 + 2 * SP * PST);
+    const uint32_t sP = sdO + SP * 128, sDS = sP + SP * PST, sO = sDS + SP * PST;
+    float* s_lse = reinterpret_cast<float*>(smem + 5 * SP * 128 + 2 * SP * PST);
     float* s_del = s_lse + SP;
     float* s_mb = s_del + SP;
     const int items = B * NH;
@@ -693,6 +693,7 @@ attention_bwd_bh_cached_kernel(const bf16* __restrict__ qkv, const long long* __
         const int b = item / NH, h = item % NH;
         load_tile_n(sQ, qkv, QKV_LD, (long long)b * S, h * HD, SP, S, blockDim.x);
         load_tile_n(sdO, dctx, HID, (long long)b * S, h * HD, SP, S, blockDim.x);
+        load_tile_n(sO, ctx, HID, (long long)b * S, h * HD, SP, S, blockDim.x);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto issue_kv = [&](int item) {
@@ -711,11 +712,25 @@ attention_bwd_bh_cached_kernel(const bf16* __restrict__ qkv, const long long* __
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         {
             const float* L = lse + ((long long)b * NH + h) * S;
-            const float* Dl = delta + ((long long)b * NH + h) * S;
             for (int i = threadIdx.x; i < SP; i += blockDim.x) {
                 s_lse[i] = i < S ? L[i] * LOG2E : INFINITY;     // +inf: padded rows contribute exp2(-inf) = 0
-                s_del[i] = i < S ? Dl[i] : 0.f;
                 s_mb[i] = i < S ? (mask[base + i] != 0 ? 0.f : MASK_LOG2) : -INFINITY;
+            }
+            // delta[q] = sum_d dO[q,d] * O[q,d].  Same (row, 16-byte chunk) -> thread mapping as load_tile_n, so
+            // every thread reads back only what its own cp.async brought in (complete after the wait above); the
+            // 8 chunks of a row sit in 8 consecutive lanes.  Rows >= S were zero-filled.
+            for (int i = threadIdx.x; i < SP * 8; i += blockDim.x) {
+                const int r = i >> 3, c = i & 7;
+                float a[8], d[8];
+                load8_bf16(reinterpret_cast<const bf16*>(smem + (sO - sQ) + tile_off(r, c)), a);
+                load8_bf16(reinterpret_cast<const bf16*>(smem + (sdO - sQ) + tile_off(r, c)), d);
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc += a[k] * d[k];
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (c == 0) s_del[r] = acc;
             }
         }
         __syncthreads();
@@ -878,20 +893,25 @@ extern "C" UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long lon
     cudaStream_t s = (cudaStream_t)stream;
     const long long rows = (long long)B * S;
     ProfScope prof(s, 1, 10.0 * B * NH * (double)S * S * HD);      // 5 S x S x 64 products (7 computed)
-    launch_pdl(attention_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, 1, (const bf16*)ctx,
-               (const bf16*)dctx, delta_ws, B, S);
-    if (int rc = check_last("attention_delta_kernel")) return rc;
+    auto launch_delta = [&]() {
+        launch_pdl(attention_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, 1, (const bf16*)ctx,
+                   (const bf16*)dctx, delta_ws, B, S);
+        return check_last("attention_delta_kernel");
+    };
     if (S <= 256) {
         const int SP = (S + 31) / 32 * 32;
-        const int smem_cached = 4 * SP * 128 + 2 * SP * (SP * 2 + 16) + 3 * SP * 4;
+        // Q K V dO O tiles + P, dS + three float vectors; delta is computed in the kernel from the O and dO tiles
+        const int smem_cached = 5 * SP * 128 + 2 * SP * (SP * 2 + 16) + 3 * SP * 4;
         if (smem_cached <= 225 * 1024) {
             if (int rc = set_smem(attention_bwd_bh_cached_kernel, smem_cached)) return rc;
             const int items = B * NH;
             const int grid = items < num_sms() ? items : num_sms();
             launch_pdl(attention_bwd_bh_cached_kernel, dim3(grid), dim3(bh_warps(S) * 32), smem_cached, s, 1,
-                       (const bf16*)qkv, attn_mask, (const bf16*)dctx, lse, delta_ws, (bf16*)dqkv, B, S, SP, drop);
+                       (const bf16*)qkv, attn_mask, (const bf16*)dctx, lse, (const bf16*)ctx, (bf16*)dqkv, B, S, SP,
+                       drop);
             return check_last("attention_bwd_bh_cached_kernel");
         }
+        if (int rc = launch_delta()) return rc;
         const int nbuf = (2 * 4 * SP * 128 + 3 * SP * 4 <= 220 * 1024) ? 2 : 1;
         const int smem_bh = nbuf * 4 * SP * 128 + 3 * SP * 4;
         if (int rc = set_smem(attention_bwd_bh_kernel, smem_bh)) return rc;
@@ -901,6 +921,7 @@ extern "C" UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long lon
                    (const bf16*)dctx, lse, delta_ws, (bf16*)dqkv, B, S, SP, nbuf, drop);
         return check_last("attention_bwd_bh_kernel");
     }
+    if (int rc = launch_delta()) return rc;
     const int smem_dq = 2 * TILE * 128 + 2 * S_pad * 128 + S_pad * 4;
     const int smem_dkv = 2 * TILE * 128 + 2 * S_pad * 128 + 2 * S_pad * 4;
     if (int rc = set_smem(attention_bwd_dq_kernel, smem_dq)) return rc;
