@@ -349,6 +349,36 @@ UC2_API int uc2_adamw_step(float* param, float* grad, float* exp_avg, float* exp
                            const uc2_opt_chunk* chunks, int n_chunks, const int* act_step, const int* group_of,
                            const uc2_adamw_hyper* hyper, const double* sqnorm, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-side batch assembly (the step before the path) for region features that are
+ * resident in HBM as a ragged arena: image i owns arena rows [row0_i, row0_i + nbb_i).
+ * uc2_pad_rows replaces pad_tensors data/data.py:360-373 (out[b, r, :] = arena row, zeros for r >= nbb_b),
+ * _mask_img_feat data/mrm.py:35-38 (zero_masked: masked rows written as zeros) and _get_feat_target 27-32 /
+ * _get_targets 213-218 (targets[tgt_slot[b, r], :] = the unmasked row; tgt_slot = exclusive row-major scan of mask).
+ * D is the row width: 2048 features, 7 box numbers, 1601 soft labels.  `out` may be NULL when only targets are wanted.
+ */
+typedef struct {
+    const float* arena;          /* [rows_total, D] */
+    int D;
+    const long long* row0;       /* [B] first arena row of each batch item */
+    const int* nbb;              /* [B] */
+    const unsigned char* mask;   /* [B, R] 1 = masked region; may be NULL */
+    const int* tgt_slot;         /* [B, R] row of `targets` for masked regions; may be NULL when targets is NULL */
+    int B, R;
+    int zero_masked;
+} uc2_pad_args;
+UC2_API int uc2_pad_rows(const uc2_pad_args* args, float* out, float* targets, void* stream);
+/* Index side of a batch from the (txt_lens, num_bbs) vectors, T = max txt_len, R = max num_bb, S = packed length:
+ *   attn_masks[b, j]   = j < tl_b + nbb_b                                   (data/itm.py:299-301 and siblings)
+ *   gather_index[b, j] = j - tl_b + T on the image block, else j            (get_gather_index data/data.py:376-384)
+ *   ot_scatter[b, j]   = j - tl_b + T for j >= tl_b, else j                 (_compute_ot_scatter data/itm.py:264-271)
+ *   txt_pad[b, m] = m >= tl_b, img_pad[b, n] = n >= nbb_b                   (_compute_pad data/itm.py:274-278)
+ *   img_mask_tgt[b, j] = img_mask[b, j - tl_b] on the image block, else 0   (_get_img_tgt_mask data/mrm.py:22-25)
+ * Any output may be NULL. */
+UC2_API int uc2_batch_index(const int* txt_lens, const int* num_bbs, const unsigned char* img_mask, int B, int T,
+                            int R, int S, long long* attn_masks, long long* gather_index, long long* ot_scatter,
+                            unsigned char* txt_pad, unsigned char* img_pad, unsigned char* img_mask_tgt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

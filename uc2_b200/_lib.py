@@ -62,6 +62,11 @@ class Dropout(C.Structure):
     _fields_ = [("attn_thresh", C.c_uint), ("attn_scale", F), ("hidden_thresh", C.c_uint), ("hidden_scale", F)]
 
 
+class PadArgs(C.Structure):
+    _fields_ = [("arena", P), ("D", I), ("row0", P), ("nbb", P), ("mask", P), ("tgt_slot", P), ("B", I), ("R", I),
+                ("zero_masked", I)]
+
+
 class OptChunk(C.Structure):
     _fields_ = [("offset", LL), ("n", I), ("tensor", I)]
 
@@ -109,6 +114,8 @@ _SIGS = {
     "uc2_f32_to_bf16_2d": [P, LL, P, LL, LL, I, P],
     "uc2_ot_ipot_fwd": [P, P, P, P, I, I, I, I, I, F, I, I, P, P, P, P],
     "uc2_ot_ipot_bwd": [P, P, P, P, I, I, I, I, I, P, P, P, P, P],
+    "uc2_pad_rows": [C.POINTER(PadArgs), P, P, P],
+    "uc2_batch_index": [P, P, P, I, I, I, I, P, P, P, P, P, P, P],
     "uc2_profile_enable": [I],
     "uc2_profile_collect": [P, P, P, I],
     "uc2_cast_f32_bf16": [P, P, LL, P],
