@@ -255,3 +255,86 @@ def test_token_bucket_sampler_and_meta_loader_match_reference(golden):
     assert [next(ia)[0] for _ in range(40)] == [next(ib)[0] for _ in range(40)]
     with pytest.raises(ValueError):
         len(TokenBucketSampler(lens, 8, 100))
+
+
+class _ScoreStub(torch.nn.Module):
+    """Stands in for the retrieval model: returns the scores the batch carries (the bookkeeping is under test)."""
+    def forward(self, batch, compute_loss=False):
+        return batch["scores"].unsqueeze(1)
+
+
+def _hn_loader(n_txt, n_img, per_batch, seed, rank=0, world=1):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for t in range(rank, n_txt, world):
+        gt = torch.Generator().manual_seed(seed * 1000 + t)
+        imgs = [f"img{i}" for i in torch.randperm(n_img, generator=gt)[:per_batch].tolist()]
+        out.append({"gt_txt_id": f"txt{t}", "neg_img_ids": imgs, "scores": torch.randn(per_batch, generator=gt)})
+    return out
+
+
+def _ref_hard_negs(batches, k):
+    """itm.py:385-445 restated literally (single process sees every batch)."""
+    from collections import defaultdict
+    txt2hardimgs, img_to_score_txts = {}, defaultdict(list)
+    for b in batches:
+        scores, txt, imgs = b["scores"], b["gt_txt_id"], b["neg_img_ids"]
+        txt2hardimgs[txt] = [imgs[i] for i in scores.topk(k, sorted=False)[1].tolist()]
+        for i, img in enumerate(imgs):
+            img_to_score_txts[img].append((scores[i].item(), txt))
+    img2hardtxts = {}
+    for img, st in img_to_score_txts.items():
+        sc, txts = [s for s, _ in st], [t for _, t in st]
+        idx = range(len(txts)) if len(txts) < k else torch.tensor(sc).topk(k, sorted=False)[1].tolist()
+        img2hardtxts[img] = [txts[i] for i in idx]
+    return txt2hardimgs, img2hardtxts
+
+
+def test_hard_negative_extraction_and_validate():
+    from uc2_b200.retrieval import get_hard_negs, validate
+    batches = _hn_loader(40, 30, 12, seed=3)
+    t2i, i2t = get_hard_negs(_ScoreStub(), batches, hard_negative_num=5)
+    rt2i, ri2t = _ref_hard_negs(batches, 5)
+    assert {k: set(v) for k, v in t2i.items()} == {k: set(v) for k, v in rt2i.items()}
+    assert {k: set(v) for k, v in i2t.items()} == {k: set(v) for k, v in ri2t.items()}
+    # validate (itm.py:447-488): ground truth is index 0 of every batch
+    vb = []
+    for r, n in ((0, 12), (3, 12), (7, 12), (11, 12), (2, 6)):      # rank of the ground truth inside the batch
+        s = torch.arange(n, 0, -1).float()                            # descending: index i has rank i
+        s[0], s[r] = s[r].item(), s[0].item()
+        vb.append({"scores": s})
+    log = validate(_ScoreStub(), vb)
+    assert log["valid/recall_1"] == 1 / 5 and log["valid/recall_5"] == 3 / 5 and log["valid/recall_10"] == 4 / 5
+
+
+HN_SCRIPT = r"""
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from uc2_b200 import distributed as D
+from uc2_b200.retrieval import get_hard_negs
+import test_host_cpu as T
+D.init("gloo")
+r, w = D.rank(), D.size()
+mine = T._hn_loader(24, 20, 8, seed=5, rank=r, world=w)
+t2i, i2t = get_hard_negs(T._ScoreStub(), mine, hard_negative_num=4)
+everything = T._hn_loader(24, 20, 8, seed=5)
+rt2i, ri2t = T._ref_hard_negs(everything, 4)
+assert {k: set(v) for k, v in t2i.items()} == {k: set(rt2i[k]) for k in t2i} and len(t2i) == 12
+if r == 0:
+    assert {k: set(v) for k, v in i2t.items()} == {k: set(v) for k, v in ri2t.items()}
+else:
+    assert i2t == {}
+dist.destroy_process_group()
+print("ok", r)
+"""
+
+
+def test_hard_negative_extraction_gloo_world2(tmp_path):
+    script = tmp_path / "hn.py"
+    script.write_text(HN_SCRIPT % (ROOT, os.path.join(ROOT, "tests")))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29741", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 2

@@ -173,3 +173,101 @@ def itm_eval(score_matrix, txt_ids, img_ids, txt2img, img2txts, column_only=Fals
     return {"txt_r1": tr[0], "txt_r5": tr[1], "txt_r10": tr[2], "txt_r_mean": tr_mean,
             "img_r1": ir[0], "img_r5": ir[1], "img_r10": ir[2], "img_r_mean": ir_mean,
             "r_mean": (tr_mean + ir_mean) / 2}
+
+
+@torch.no_grad()
+def validate(model, val_loader):
+    """itm.py:447-488: every batch is one caption against `mini_batch_size` images with the ground truth FIRST; the
+    rank of index 0 inside the top-10 gives recall@1/5/10.  The reference pulls `rank.item()` to the host per batch;
+    here the three counters live on the device and are read once."""
+    import time
+    was_training = model.training
+    model.eval()
+    st = time.time()
+    counts, n_ex = None, 0
+    for batch in val_loader:
+        scores = model(batch, compute_loss=False).squeeze(1)
+        _, indices = scores.topk(min(10, scores.numel()), dim=0)
+        hit = indices == 0
+        pos = torch.where(hit.any(), hit.float().argmax(), torch.full((), 10, device=scores.device))
+        c = torch.stack([pos < 1, pos < 5, pos < 10]).long()
+        counts = c if counts is None else counts + c
+        n_ex += 1
+    r = [0, 0, 0] if counts is None else [int(x) for x in counts.tolist()]
+    n_all = sum(D.all_gather_list(n_ex))
+    r = [sum(D.all_gather_list(x)) / max(n_all, 1) for x in r]
+    tot = time.time() - st
+    if was_training:
+        model.train()
+    return {"valid/ex_per_s": n_all / tot, "valid/recall_1": r[0], "valid/recall_5": r[1], "valid/recall_10": r[2]}
+
+
+def hardest_per_group(scores, group, k):
+    """For every distinct value of `group` (int64 [N]) the indices of its (up to) k largest `scores` (descending,
+    ties by first occurrence).  Returns (sel [M] indices into scores, grouped by ascending group value, sizes dict
+    is implied by group[sel]).  Works on any device: two stable sorts and a segmented position."""
+    order = torch.argsort(scores, descending=True, stable=True)
+    order = order[torch.argsort(group[order], stable=True)]          # by group, score-descending inside each group
+    g = group[order]
+    start = torch.ones_like(g, dtype=torch.bool)
+    start[1:] = g[1:] != g[:-1]
+    idx = torch.arange(g.numel(), device=g.device)
+    first = torch.cummax(torch.where(start, idx, torch.zeros_like(idx)), 0)[0]
+    return order[(idx - first) < k]
+
+
+@torch.no_grad()
+def get_hard_negs(model, loader, hard_negative_num=20, all_img_ids=None):
+    """itm.py:385-445.  Each batch: one caption (`gt_txt_id`) scored against `neg_img_ids` images.
+    txt2hardimgs[txt] = the `hard_negative_num` best-scoring images of that caption; img2hardtxts[img] = the
+    `hard_negative_num` best-scoring captions of that image over ALL ranks (rank 0 only, like the reference; fewer
+    when an image met fewer captions).  The reference calls topk(sorted=False), whose order is unspecified: lists
+    here are in descending score order.  Scores stay on the device until the end (the reference calls .item() per
+    pair); the per-image selection is two device sorts instead of a Python loop over images."""
+    was_training = model.training
+    model.eval()
+    txt2hardimgs = {}
+    img_index, txt_list, hard_idx = {}, [], []
+    all_scores, all_img, all_txt = [], [], []
+    for batch in loader:
+        scores = model(batch, compute_loss=False).squeeze(-1).float()
+        txt, imgs = batch["gt_txt_id"], batch["neg_img_ids"]
+        assert scores.numel() == len(imgs)
+        k = min(hard_negative_num, len(imgs))
+        hard_idx.append(scores.topk(k)[1])                            # device indices, resolved after the loop
+        t = len(txt_list)
+        txt_list.append((txt, imgs))
+        all_scores.append(scores)
+        all_img.append(torch.tensor([img_index.setdefault(i, len(img_index)) for i in imgs], dtype=torch.long))
+        all_txt.append(torch.full((len(imgs),), t, dtype=torch.long))
+    for (txt, imgs), hi in zip(txt_list, hard_idx):
+        txt2hardimgs[txt] = [imgs[i] for i in hi.tolist()]
+    # hard texts per image: pairs from every rank
+    local_imgs = sorted(img_index, key=img_index.get)
+    if all_scores:
+        sc = torch.cat(all_scores).cpu()
+        pairs = (sc, torch.cat(all_img), torch.cat(all_txt))
+    else:
+        pairs = (torch.zeros(0), torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long))
+    gathered = D.all_gather_list((pairs, local_imgs, [t for t, _ in txt_list]))
+    if was_training:
+        model.train()
+    if D.rank() != 0:
+        return txt2hardimgs, {}
+    gimg, scs, gi, gt, txt_names = {}, [], [], [], []
+    for (sc, im, tx), names, txts in gathered:
+        remap = torch.tensor([gimg.setdefault(n, len(gimg)) for n in names], dtype=torch.long)
+        scs.append(sc)
+        gi.append(remap[im] if im.numel() else im)
+        gt.append(tx + len(txt_names))
+        txt_names.extend(txts)
+    sc, gi, gt = torch.cat(scs), torch.cat(gi), torch.cat(gt)
+    dev = all_scores[0].device if all_scores else "cpu"
+    sel = hardest_per_group(sc.to(dev), gi.to(dev), hard_negative_num).cpu()
+    names = sorted(gimg, key=gimg.get)
+    img2hardtxts = {}
+    for i, t in zip(gi[sel].tolist(), gt[sel].tolist()):
+        img2hardtxts.setdefault(names[i], []).append(txt_names[t])
+    for img in (all_img_ids if all_img_ids is not None else names):
+        img2hardtxts.setdefault(img, [])
+    return txt2hardimgs, img2hardtxts
