@@ -338,3 +338,83 @@ def test_hard_negative_extraction_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2
+
+
+class _OutStub(torch.nn.Module):
+    """Returns the output the batch carries: the validation bookkeeping is under test, not the model."""
+    def forward(self, batch, task=None, compute_loss=True):
+        return batch["_out"]
+
+
+def test_validation_loops_match_reference_formulas():
+    """uc2_b200.validate against the formulas of pretrain.py:688-1050 written out with the reference's per-batch
+    .item() accumulation."""
+    import torch.nn.functional as F
+    from uc2_b200 import validate as V
+    g = torch.Generator().manual_seed(1)
+    m = _OutStub()
+
+    def rn(*s):
+        return torch.randn(*s, generator=g)
+
+    # token tasks (validate_mlm / mmxlm / vmlm)
+    bs = []
+    for n in (7, 12):
+        lab = torch.full((4, 9), -1, dtype=torch.long)
+        flat = torch.randperm(36, generator=g)[:n]
+        lab.view(-1)[flat] = torch.randint(0, 50, (n,), generator=g)
+        bs.append({"_out": rn(n, 50), "txt_labels": lab})
+    loss = correct = words = 0
+    for b in bs:
+        l = b["txt_labels"][b["txt_labels"] != -1]
+        loss += F.cross_entropy(b["_out"], l, reduction="sum").item()
+        correct += (b["_out"].max(dim=-1)[1] == l).sum().item()
+        words += l.numel()
+    for fn in (V.validate_mlm, V.validate_mmxlm, V.validate_vmlm):
+        log = fn(m, bs)
+        assert set(log) == {"loss", "acc", "tok_per_s"}
+        np.testing.assert_allclose([log["loss"], log["acc"]], [loss / words, correct / words], rtol=1e-6)
+    # soft-label tasks and MRC (kl and plain)
+    bs = []
+    for n in (5, 8):
+        tgt = torch.softmax(rn(n, 30) * 3, -1)
+        mask = torch.zeros(3, 10, dtype=torch.bool)
+        mask.view(-1)[:n] = True
+        bs.append({"_out": rn(n, 30), "label_targets": tgt, "tgt_masks": mask, "img_mask_tgt": mask})
+    loss = score = feats = 0
+    for b in bs:
+        p = F.log_softmax(b["_out"], dim=-1)
+        loss += F.kl_div(p, b["label_targets"], reduction="sum").item()
+        score += (p.max(dim=-1)[1] == b["label_targets"].max(dim=-1)[1]).sum().item()
+        feats += b["tgt_masks"].sum().item()
+    for log in (V.validate_mmxlm_soft(m, bs), V.validate_vmlm_soft(m, bs), V.validate_mrc(m, bs, "mrc-kl")):
+        assert set(log) == {"loss", "acc", "feat_per_s"}
+        np.testing.assert_allclose([log["loss"], log["acc"]], [loss / feats, score / feats], rtol=1e-6)
+    loss = score = 0
+    for b in bs:
+        cls = b["label_targets"][:, 1:].max(dim=-1)[1] + 1
+        loss += F.cross_entropy(b["_out"], cls, ignore_index=0, reduction="sum").item()
+        score += (b["_out"][:, 1:].max(dim=-1)[1] == b["label_targets"][:, 1:].max(dim=-1)[1]).sum().item()
+    log = V.validate_mrc(m, bs, "mrc")
+    np.testing.assert_allclose([log["loss"], log["acc"]], [loss / feats, score / feats], rtol=1e-6)
+    # MRFR
+    bs = [{"_out": rn(n, 2048) ** 2, "img_mask_tgt": torch.ones(n, dtype=torch.bool)} for n in (3, 6)]
+    log = V.validate_mrfr(m, bs)
+    want = sum(b["_out"].sum().item() / 2048 for b in bs) / 9
+    np.testing.assert_allclose(log["loss"], want, rtol=1e-6)
+    # ITM with the (pos, neg) OT pair
+    bs = [{"_out": (rn(n, 2), (rn(3).abs(), rn(n - 3).abs())), "targets": torch.randint(0, 2, (n,), generator=g)}
+          for n in (6, 9)]
+    loss = score = ot = otp = otn = 0
+    for b in bs:
+        sc, (p, q) = b["_out"]
+        loss += F.cross_entropy(sc, b["targets"], reduction="sum").item()
+        score += (sc.max(dim=-1)[1] == b["targets"]).sum().item()
+        otp += p.sum().item(); otn += q.sum().item(); ot += p.sum().item() - q.sum().item()
+    log = V.validate_itm(m, bs)
+    np.testing.assert_allclose([log["valid/loss"], log["valid/acc"], log["valid/ot_loss"], log["valid/ot_pos"],
+                                log["valid/ot_neg"]], [loss / 15, score / 15, ot / 15, otp / 15, otn / 15], rtol=1e-5)
+    assert "valid/ot_loss" not in V.validate_itm(m, [{"_out": (rn(4, 2), None), "targets": torch.zeros(4, dtype=torch.long)}])
+    # dispatcher: prefixes and key naming of pretrain.py:658-685
+    out = V.validate(m, {"mrfr_coco": [{"_out": rn(3, 2048), "img_mask_tgt": torch.ones(3, dtype=torch.bool)}]})
+    assert set(out["mrfr_coco"]) == {"mrfr_coco_loss", "mrfr_coco_feat_per_s"}

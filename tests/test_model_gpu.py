@@ -490,3 +490,28 @@ def test_prefetcher_order_and_contents():
                     assert torch.equal(d[k][kk].cpu(), vv) if torch.is_tensor(vv) else d[k][kk] == vv
             else:
                 assert d[k] == v
+
+
+def test_validation_loops_on_the_real_model(golden):
+    """uc2_b200.validate (pretrain.py:658-1050) over real batches: the per-task validation loss equals the golden
+    training loss of the same batch where the two are the same quantity (mean CE / KL per target, dropout off)."""
+    from uc2_b200 import validate as V
+    g = golden("pretrain")
+    cfg = cases.config(2)
+    m, _ = build("pretrain", cfg, "vlxlmr")
+    m.eval()
+    loaders = {"mlm": [dev(cases.batch_mlm())], "mrfr": [dev(cases.batch_mrfr())], "mrc-kl": [dev(cases.batch_mrc())],
+               "itm": [dev(cases.batch_itm())], "mmxlm": [dev(cases.batch_mmxlm())]}
+    out = V.validate(m, loaders)
+    assert not m.training
+    np.testing.assert_allclose(out["mlm"]["mlm_loss"], g["mlm|loss"][0], rtol=LOSS_RTOL * 3)
+    np.testing.assert_allclose(out["mmxlm"]["mmxlm_loss"], g["mmxlm|loss"][0], rtol=LOSS_RTOL * 3)
+    # KL: the training loss averages over all [n, 1601] elements, validation divides the sum by n
+    kl = g["mrc-kl|loss_vec"]
+    np.testing.assert_allclose(out["mrc-kl"]["mrc-kl_loss"], float(kl.sum()) / kl.shape[0], rtol=LOSS_RTOL * 3, atol=1e-4)
+    # MRFR: sum of the per-element squared errors / 2048 / n_masked == mean of the loss vector
+    np.testing.assert_allclose(out["mrfr"]["mrfr_loss"], g["mrfr|loss"][0], rtol=LOSS_RTOL * 3, atol=1e-4)
+    np.testing.assert_allclose(out["itm"]["itm_valid/loss"], float(np.mean(g["itm|itm_loss"])), atol=1e-2)
+    for k in ("itm_valid/acc", "itm_valid/ot_loss", "itm_valid/ot_pos", "itm_valid/ot_neg"):
+        assert k in out["itm"]
+    assert 0.0 <= out["mlm"]["mlm_acc"] <= 1.0
