@@ -418,3 +418,110 @@ def test_validation_loops_match_reference_formulas():
     # dispatcher: prefixes and key naming of pretrain.py:658-685
     out = V.validate(m, {"mrfr_coco": [{"_out": rn(3, 2048), "img_mask_tgt": torch.ones(3, dtype=torch.bool)}]})
     assert set(out["mrfr_coco"]) == {"mrfr_coco_loss", "mrfr_coco_feat_per_s"}
+
+
+def test_pretrain_loop_bookkeeping_matches_reference_loop():
+    """uc2_b200.pretrain_loop.PretrainLoop with the training step stubbed out: meters, counters, logging points,
+    validation / checkpoint cadence against pretrain.py:484-656 restated with its per-step .item() calls."""
+    import math
+    from types import SimpleNamespace
+    from uc2_b200.pretrain_loop import PretrainLoop, RunningMeter
+    g = torch.Generator().manual_seed(4)
+    opts = SimpleNamespace(gradient_accumulation_steps=2, num_train_steps=5, valid_steps=2, grad_norm=2.0,
+                           itm_ot_lambda=0.1, ot_pos_only=False, learning_rate=1e-4, decay="linear", warmup_steps=2)
+    stream = []
+    for i in range(14):
+        B, S = 4 + i % 3, 10
+        attn = (torch.rand(B, S, generator=g) > 0.3).long()
+        if i % 3 == 0:
+            npos = 0 if i == 6 else 2                                   # one batch without positives: NaN mean dropped
+            out = (torch.rand(B, generator=g), (torch.rand(npos, generator=g), torch.rand(B - npos, generator=g)))
+            name = "itm_coco"
+        else:
+            out = torch.rand(3 + i, generator=g)
+            name = "mlm_coco" if i % 3 == 1 else "mrfr_vg"
+        stream.append((name, {"input_ids": torch.zeros(B, 6, dtype=torch.long), "attn_masks": attn, "_out": out}))
+
+    class FakeStep(object):
+        def __init__(self):
+            self.global_step, self.micro, self.last_out, self.last_grad_norm = 0, 0, None, None
+        def __call__(self, batch, task):
+            from uc2_b200.train import reduce_loss
+            self.last_out = batch["_out"]
+            self.micro += 1
+            if self.micro % opts.gradient_accumulation_steps == 0:
+                self.global_step += 1
+                self.last_grad_norm = torch.tensor(1.5)
+            return reduce_loss(batch["_out"], task, opts.itm_ot_lambda)
+
+    class Saver(object):
+        calls = []
+        def save(self, model, step, optimizer=None):
+            self.calls.append((step, optimizer is not None))
+
+    class Restorer(object):
+        global_step, n = 0, 0
+        def step(self):
+            Restorer.n += 1
+
+    logged = []
+    model = torch.nn.Linear(1, 1)
+    loop = PretrainLoop(model, SimpleNamespace(param_groups=[{"lr": 0.1}]), opts, val_dataloaders={},
+                        model_saver=Saver(), restorer=Restorer(), scalar_log=lambda n, v, s: logged.append((n, v, s)),
+                        log_every=2, step_fn=FakeStep())
+    end = loop.run(iter(stream), task_names=["itm_coco", "mlm_coco", "mrfr_vg"])
+    assert end == 5
+    # ---- the reference loop, literally
+    meters = {}
+    def meter(k):
+        return meters.setdefault(k, RunningMeter(f"loss/{k}"))
+    for t in ("itm_coco", "mlm_coco", "mrfr_vg", "itm_coco_xe", "itm_coco_ot", "itm_coco_ot_pos", "itm_coco_ot_neg"):
+        meter(t)
+    n_ex, n_in, n_l = {}, {}, {}
+    gs, snaps = 0, {}
+    for step, (name, b) in enumerate(stream):
+        n_ex[name] = n_ex.get(name, 0) + b["input_ids"].size(0)
+        n_in[name] = n_in.get(name, 0) + (b["attn_masks"] == 1).sum().item()
+        loss = b["_out"]
+        if name.startswith("itm"):
+            itm_loss, (pos, neg) = loss
+            n_l[name] = n_l.get(name, 0) + itm_loss.size(0)
+            itm_loss = itm_loss.mean()
+            ot = (pos.sum() - neg.sum()) / (pos.size(0) + neg.size(0))
+            p = pos.mean().item()
+            if not math.isnan(p):
+                meter(f"{name}_ot_pos")(p)
+            q = neg.mean().item()
+            if not math.isnan(q):
+                meter(f"{name}_ot_neg")(q)
+            loss = itm_loss + opts.itm_ot_lambda * ot
+            meter(f"{name}_xe")(itm_loss.item())
+            meter(f"{name}_ot")(ot.item())
+        else:
+            n_l[name] = n_l.get(name, 0) + loss.size(0)
+            loss = loss.mean()
+        meter(name)(loss.item())
+        if (step + 1) % 2 == 0:
+            gs += 1
+            snaps[gs] = {m.name: m.val for m in meters.values() if m.val is not None}
+        if gs >= opts.num_train_steps:
+            break
+    assert dict(loop.n_examples) == n_ex and dict(loop.n_in_units) == n_in and dict(loop.n_loss_units) == n_l
+    for k, m in meters.items():
+        got = loop.task2loss[k].val
+        assert (got is None) == (m.val is None), k
+        if got is not None:
+            np.testing.assert_allclose(got, m.val, rtol=1e-6, err_msg=k)
+    # logging points: every 2 optimizer steps the meters as of that step
+    for s in (2, 4):
+        got = {n: v for n, v, st in logged if st == s and n.startswith("loss/")}
+        assert set(got) == set(snaps[s])
+        for n in got:
+            np.testing.assert_allclose(got[n], snaps[s][n], rtol=1e-6, err_msg=f"{n}@{s}")
+        assert ("grad_norm", 1.5, s) in logged
+        assert {n for n, _, st in logged if st == s and n.startswith("perf/")} == {
+            f"perf/{t}_{u}_per_s" for t in ("itm_coco", "mlm_coco", "mrfr_vg") for u in ("ex", "in", "loss")}
+    assert [s for n, _, s in logged if n == "lr"] == [1, 2, 3, 4, 5]
+    # validation + checkpoint at steps 2 and 4 (with optimizer state) and once more at the end (5, model only)
+    assert Saver.calls == [(2, True), (4, True), (5, False)] and Restorer.n == 5
+    assert model.training

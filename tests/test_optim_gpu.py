@@ -181,3 +181,52 @@ def test_checkpoint_resume_is_exact(tmp_path):
     moved = float((p1["roberta.encoder.layer.0.output.dense.weight"].detach().cpu()
                    - p0["roberta.encoder.layer.0.output.dense.weight"]).abs().mean())
     assert moved > 1e-4
+
+
+def test_pretrain_loop_end_to_end(tmp_path):
+    """PretrainLoop (pretrain.py:484-656) on the real model: MetaLoader task schedule, accumulation 2, validation and
+    checkpoints every 2 optimizer steps, meters and throughput counters filled without per-step host reads."""
+    from types import SimpleNamespace
+    from uc2_b200 import model
+    from uc2_b200.batch import to_device
+    from uc2_b200.loader import MetaLoader
+    from uc2_b200.optim import AdamW
+    from uc2_b200.pretrain_loop import PretrainLoop
+    from uc2_b200.save import ModelSaver
+    from uc2_b200.utils import set_dropout
+    cfg = cases.config(2)
+    m = model.VLXLMRForPretraining(cfg, 2048, 1601)
+    m.load_state_dict(cases.with_aliases(cases.weights(cfg, "pretrain"), "pretrain"), strict=False)
+    m.cuda().train()
+    set_dropout(m, 0)
+    opt = AdamW([{"params": list(m.parameters()), "weight_decay": 0.01}], lr=1e-4, betas=(0.9, 0.98))
+    opts = SimpleNamespace(gradient_accumulation_steps=2, num_train_steps=3, valid_steps=2, grad_norm=5.0,
+                           itm_ot_lambda=0.1, ot_pos_only=False, learning_rate=1e-4, decay="linear", warmup_steps=1)
+    train = {"mlm_coco": [to_device(cases.batch_mlm(seed=s), "cuda") for s in (8, 18)],
+             "mrfr_coco": [to_device(cases.batch_mrfr(seed=s), "cuda") for s in (9, 19)],
+             "itm_coco": [to_device(cases.batch_itm(seed=s), "cuda") for s in (7, 17)]}
+    val = {"mlm_coco": [to_device(cases.batch_mlm(seed=28), "cuda")],
+           "itm_coco": [to_device(cases.batch_itm(seed=27), "cuda")]}
+    logged, lines = [], []
+    loop = PretrainLoop(m, opt, opts, val_dataloaders=val, model_saver=ModelSaver(str(tmp_path)),
+                        scalar_log=lambda n, v, s: logged.append((n, v, s)), log=lines.append, log_every=1)
+    import random
+    random.seed(3)
+    end = loop.run(MetaLoader(train, accum_steps=2))
+    assert end == 3 and opt.global_step == 3
+    for s, with_opt in ((2, True), (3, False)):
+        assert os.path.exists(tmp_path / f"model_step_{s}.pt")
+        assert os.path.exists(tmp_path / f"train_state_{s}.pt") == with_opt
+    seen = {k for k, mtr in loop.task2loss.items() if mtr.val is not None}
+    assert seen and all(np.isfinite(loop.task2loss[k].val) for k in seen)
+    tasks_run = {k for k in loop.n_examples}
+    assert sum(loop.n_examples.values()) == 6 * 6                       # 6 micro-steps of 6 samples
+    for t in tasks_run:
+        assert loop.n_in_units[t] > 0
+        if t.startswith("itm"):
+            assert {f"{t}_xe", f"{t}_ot", f"{t}_ot_pos", f"{t}_ot_neg"} <= seen
+    names = {n for n, _, _ in logged}
+    assert "lr" in names and "grad_norm" in names and any(n.startswith("valid_mlm_coco/") for n in names)
+    assert any(n.startswith("valid_itm_coco/itm_coco_valid/") for n in names)
+    assert any("examples trained" in l for l in lines)
+    assert m.training

@@ -47,6 +47,8 @@ class TrainStep(object):
         self.bucket_bytes = bucket_bytes
         self.layers_per_segment = layers_per_segment
         self.sync = None
+        self.last_out = None              # raw model output of the last micro-step (for loop bookkeeping)
+        self.last_grad_norm = None        # device scalar: total gradient norm before clipping, last optimizer step
 
     def _ensure_sync(self):
         arena = self.model._arena()
@@ -66,6 +68,7 @@ class TrainStep(object):
         out = self.model(batch, task=task, compute_loss=True) if task is not None else self.model(batch, compute_loss=True)
         loss = reduce_loss(out, task, self.lam, getattr(self.model, "ot_pos_only", False))
         loss.backward()
+        self.last_out = out
         self.micro += 1
         if last:
             if self.sync is not None:
@@ -77,7 +80,7 @@ class TrainStep(object):
                 for g in self.optimizer.param_groups:
                     g["lr"] = lr
             if self.grad_norm != -1 and self.grad_norm > 0:
-                clip_grad_norm_(self.optimizer, self.grad_norm)
+                self.last_grad_norm = clip_grad_norm_(self.optimizer, self.grad_norm)
             self.optimizer.step()
             self.optimizer.zero_grad()
         return loss.detach()
