@@ -482,7 +482,7 @@ def main():
     # token ids and three integers per sample, the padded batch is assembled by uc2_pad_rows / uc2_batch_index.
     # Reported beside `e2e`, never instead of it.
     hbm_store = None
-    if args.workload == "itm":
+    if args.workload == "itm" and world == 1:       # single process only: a rank-local failure must not strand NCCL
         try:
             from uc2_b200.device_batch import DeviceCollator, FeatureArena
             store = FeatureArena.synthetic(1024, (NBB, NBB), seed=11 + rank, device=dev)
