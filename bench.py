@@ -47,6 +47,24 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+def ncu_traffic(path=os.path.join(ROOT, "profiles", "r01d_gemm_ncu.txt")):
+    """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the launches of the
+    committed `ncu --set full` capture of the running step); None when the summary is not there."""
+    try:
+        tot, n = 0.0, 0
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        with open(path) as f:
+            for line in f:
+                t = line.split()
+                if "gemm_bf16_kernel" in line:
+                    n += 1
+                elif len(t) == 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and n:
+                    tot += float(t[1]) * scale.get(t[2], 1.0)
+        return (tot / n, os.path.relpath(path, ROOT)) if n else (None, None)
+    except OSError:
+        return None, None
+
+
 def flops_per_sample_fwd(S, layers=12):
     """linear 14.156 MFLOP/token/layer + attention 3072*S FLOP/token/layer."""
     return S * layers * (14155776 + 3072 * S)
@@ -521,7 +539,8 @@ def main():
             "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
             "launches_per_step": int(n_k[0]), "gemm_ms_per_step": ms_k[0], "gemm_share_of_step": ms_k[0] / ms_step,
             "attention_ms_per_step": ms_k[1],
-            "attention_tflops": work_k[1] / (ms_k[1] * 1e-3) / 1e12 if ms_k[1] > 0 else 0.0, "traffic": None}
+            "attention_tflops": work_k[1] / (ms_k[1] * 1e-3) / 1e12 if ms_k[1] > 0 else 0.0}
+    roof["traffic"], roof["traffic_source"] = ncu_traffic()
 
     if world > 1:
         torch.distributed.barrier()
