@@ -182,7 +182,8 @@ UC2_API int uc2_colsum_bf16(const void* x, long long ld, long long rows, int col
  */
 UC2_API int uc2_attention_fwd(const void* qkv, const long long* attn_mask, void* ctx, float* lse, int B, int S,
                               void* stream);
-/* dqkv: bf16 [B*S, 2304] (fully overwritten). delta_ws: fp32 [B,12,S] scratch. */
+/* dqkv: bf16 [B*S, 2304] (fully overwritten). delta_ws: fp32 [B,12,S] scratch (rowsum(dO * O); only written for
+ * S > 160, shorter sequences compute it inside the backward kernel). */
 UC2_API int uc2_attention_bwd(const void* qkv, const long long* attn_mask, const void* ctx, const void* dctx,
                               const float* lse, float* delta_ws, void* dqkv, int B, int S, void* stream);
 

@@ -3,7 +3,7 @@
 // in model/model.py:1148,1164.  The input row is bf16 (heads) or fp32 (the encoder keeps its residual
 // stream -- the LayerNorm inputs and outputs -- in fp32 so that rounding does not accumulate across the
 // 12 layers; the bf16 copy of the output is the tensor-core operand of the next GEMM).
-// HBM-bound: one warp per row, 16/32-byte accesses.
+// HBM-bound: forward one warp per row, backward two warps per row, 16/32-byte accesses.
 #include "common.cuh"
 #include "ptx.cuh"
 
