@@ -311,7 +311,23 @@ def case_loader():
     return out
 
 
+SCHED_OPTS = [dict(decay=d, learning_rate=3e-4, xlmr_lr=1e-5, warmup_steps=10, num_train_steps=50, warm_int=4,
+                   decay_int=7, decay_st=20, decay_rate=0.5) for d in ("linear", "invsqrt", "constant", "vqa")]
+
+
+def case_sched():
+    """optim/sched.py get_lr_sched / get_xlmr_lr_sched for steps 0..59 under every decay mode (incl. the <= 0 guard)."""
+    import types
+    out = {}
+    for o in SCHED_OPTS:
+        ns = types.SimpleNamespace(**o)
+        out[f"{o['decay']}|lr"] = np.array([R.sched.get_lr_sched(s, ns) for s in range(60)], dtype=np.float64)
+        out[f"{o['decay']}|xlmr_lr"] = np.array([R.sched.get_xlmr_lr_sched(s, ns) for s in range(60)], dtype=np.float64)
+    return out
+
+
 CASES = {
+    "sched": case_sched,
     "loader": case_loader,
     "retrieval": case_retrieval,
     "pretrain": lambda: case_pretrain("vlxlmr"),

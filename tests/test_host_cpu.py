@@ -525,3 +525,73 @@ def test_pretrain_loop_bookkeeping_matches_reference_loop():
     # validation + checkpoint at steps 2 and 4 (with optimizer state) and once more at the end (5, model only)
     assert Saver.calls == [(2, True), (4, True), (5, False)] and Restorer.n == 5
     assert model.training
+
+
+def test_lr_schedules_match_reference(golden):
+    """optim/sched.py (tests/golden/sched.npz was produced by the reference module itself)."""
+    from types import SimpleNamespace
+    from uc2_b200.optim import get_lr_sched, get_xlmr_lr_sched
+    g = golden("sched")
+    for decay in ("linear", "invsqrt", "constant", "vqa"):
+        o = SimpleNamespace(decay=decay, learning_rate=3e-4, xlmr_lr=1e-5, warmup_steps=10, num_train_steps=50,
+                            warm_int=4, decay_int=7, decay_st=20, decay_rate=0.5)
+        np.testing.assert_array_equal([get_lr_sched(s, o) for s in range(60)], g[f"{decay}|lr"])
+        np.testing.assert_array_equal([get_xlmr_lr_sched(s, o) for s in range(60)], g[f"{decay}|xlmr_lr"])
+
+
+def test_finetune_loop_control_flow():
+    """uc2_b200.pretrain_loop.FinetuneLoop against itm.py:253-358: separate learning rates, validation / checkpoint
+    cadence, loader rebuild after hard-negative mining, accumulation."""
+    from types import SimpleNamespace
+    from uc2_b200.optim import get_lr_sched, get_xlmr_lr_sched
+    from uc2_b200.pretrain_loop import FinetuneLoop, RunningMeter
+    opts = SimpleNamespace(gradient_accumulation_steps=2, num_train_steps=7, valid_steps=3, grad_norm=2.0,
+                           learning_rate=1e-3, xlmr_lr=1e-5, decay="linear", warmup_steps=2, separate_lr=True,
+                           steps_per_hard_neg=4)
+    optimizer = SimpleNamespace(param_groups=[{"lr": 0.0} for _ in range(4)])
+    g = torch.Generator().manual_seed(2)
+    losses = torch.rand(64, generator=g)
+
+    class FakeStep(object):
+        def __init__(self):
+            self.global_step, self.micro, self.last_grad_norm, self.seen = 0, 0, None, []
+        def __call__(self, batch, task):
+            assert task is None
+            self.seen.append(batch["i"])
+            self.micro += 1
+            if self.micro % 2 == 0:
+                self.global_step += 1
+                self.last_grad_norm = torch.tensor(0.5)
+            return losses[batch["i"]]
+
+    built, events, logged = [], [], []
+    def build_loader():
+        built.append(len(built))
+        base = 20 * (len(built) - 1)
+        return [{"input_ids": torch.zeros(3, 5, dtype=torch.long), "i": base + k} for k in range(20)]
+
+    class Saver(object):
+        def save(self, model, step, optimizer=None):
+            events.append(("save", step))
+
+    step = FakeStep()
+    loop = FinetuneLoop(torch.nn.Linear(1, 1), optimizer, opts, build_loader,
+                        validate_fn=lambda m: events.append(("val", step.global_step)) or {"valid/recall_1": 0.5},
+                        hard_neg_fn=lambda m: events.append(("hn", step.global_step)), model_saver=Saver(),
+                        scalar_log=lambda n, v, s: logged.append((n, v, s)), log_every=2, step_fn=step)
+    assert loop.run() == 7
+    # loader 0 runs until optimizer step 4 (8 micro-steps), then hard negatives are mined and the loader is rebuilt
+    assert built == [0, 1] and step.seen == list(range(8)) + list(range(20, 26))
+    assert events == [("val", 3), ("save", 3), ("hn", 4), ("val", 6), ("save", 6)]
+    assert loop.n_examples == 14 * 3
+    ref = RunningMeter("loss")
+    for i in step.seen:
+        ref(losses[i].item())
+    np.testing.assert_allclose(loop.running_loss.val, ref.val, rtol=1e-6)
+    for s in range(1, 8):
+        assert ("lr", get_lr_sched(s, opts), s) in logged and ("xlmr_lr", get_xlmr_lr_sched(s, opts), s) in logged
+    assert [s for n, _, s in logged if n == "perf/ex_per_s"] == [2, 4, 6]
+    assert ("valid/recall_1", 0.5, 3) in logged
+    # the per-group learning rates TrainStep would install
+    lrs = loop.lr_fn(3)
+    assert lrs == [get_xlmr_lr_sched(3, opts)] * 2 + [get_lr_sched(3, opts)] * 2

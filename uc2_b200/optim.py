@@ -239,15 +239,34 @@ def warmup_linear(step, warmup_step, tot_step):
     return max(0, (tot_step - step) / (tot_step - warmup_step))
 
 
-def get_lr_sched(global_step, opts):
+def vqa_schedule(step, warmup_interval, decay_interval, decay_start, decay_rate):
+    """optim/sched.py:19-31 (the MCAN schedule: three warm-up plateaus, then stepwise decay)."""
+    if step < 3 * warmup_interval:
+        return (step // warmup_interval + 1) / 4
+    if step >= decay_start:
+        return decay_rate ** ceil((step - decay_start) / decay_interval)
+    return 1
+
+
+def _sched(base_lr, global_step, opts):
     if opts.decay == "linear":
-        lr_this_step = opts.learning_rate * warmup_linear(global_step, opts.warmup_steps, opts.num_train_steps)
+        lr = base_lr * warmup_linear(global_step, opts.warmup_steps, opts.num_train_steps)
     elif opts.decay == "invsqrt":
-        lr_this_step = opts.learning_rate * noam_schedule(global_step, opts.warmup_steps)
+        lr = base_lr * noam_schedule(global_step, opts.warmup_steps)
     elif opts.decay == "constant":
-        lr_this_step = opts.learning_rate
+        lr = base_lr
+    elif opts.decay == "vqa":
+        lr = base_lr * vqa_schedule(global_step, opts.warm_int, opts.decay_int, opts.decay_st, opts.decay_rate)
     else:
         raise ValueError("unsupported decay")
-    if lr_this_step <= 0:
-        lr_this_step = 1e-8
-    return lr_this_step
+    return lr if lr > 0 else 1e-8         # guard against a miscounted num_train_steps (sched.py:48-50)
+
+
+def get_lr_sched(global_step, opts):
+    """optim/sched.py:34-51."""
+    return _sched(opts.learning_rate, global_step, opts)
+
+
+def get_xlmr_lr_sched(global_step, opts):
+    """optim/sched.py:53-70: the same schedules on `opts.xlmr_lr` (itm.py --separate_lr: encoder groups)."""
+    return _sched(opts.xlmr_lr, global_step, opts)

@@ -178,3 +178,100 @@ class PretrainLoop(object):
         if self.global_step % o.valid_steps != 0:
             self._validate_and_save(with_optimizer=False)
         return self.global_step
+
+
+class FinetuneLoop(object):
+    """The retrieval fine-tuning loop of itm.py:253-358: one task, triplet loss, optional separate learning rate for
+    the encoder groups (--separate_lr: the first two parameter groups follow `opts.xlmr_lr`), validation (`validate`
+    or the full `evaluate`) + checkpoint every `valid_steps`, and a rebuild of the loader after hard negatives were
+    re-mined (`steps_per_hard_neg`).
+
+    `opts`: gradient_accumulation_steps, num_train_steps, valid_steps, grad_norm, learning_rate, decay, warmup_steps,
+    and optionally separate_lr / xlmr_lr / steps_per_hard_neg.  `build_loader()` returns a fresh iterable of batches
+    (the reference re-creates its DataLoader at every pass).  `validate_fn(model) -> dict` and
+    `hard_neg_fn(model)` are the caller's closures over their datasets.
+
+    As in PretrainLoop the loss stays on the device between logging points; the reference additionally pickles its
+    RunningMeter through an all-gather EVERY optimizer step to average it over ranks (itm.py:297-299) -- here the
+    cross-rank mean is taken when the value is logged."""
+
+    def __init__(self, model, optimizer, opts, build_loader, validate_fn=None, hard_neg_fn=None, model_saver=None,
+                 restorer=None, log=None, scalar_log=None, log_every=100, step_fn=None):
+        from .optim import get_xlmr_lr_sched
+        self.model, self.optimizer, self.opts = model, optimizer, opts
+        self.build_loader, self.validate_fn, self.hard_neg_fn = build_loader, validate_fn, hard_neg_fn
+        self.model_saver, self.restorer = model_saver, restorer
+        self.log = log or (lambda msg: None)
+        self.scalar_log = scalar_log or (lambda name, value, step: None)
+        self.log_every = log_every
+
+        def lr_fn(s):
+            lr = get_lr_sched(s, opts)
+            if getattr(opts, "separate_lr", False):
+                x = get_xlmr_lr_sched(s, opts)
+                return [x if i < 2 else lr for i in range(len(optimizer.param_groups))]
+            return lr
+        self.lr_fn = lr_fn
+        self.step_fn = step_fn or TrainStep(model, optimizer, grad_norm=opts.grad_norm,
+                                            gradient_accumulation_steps=opts.gradient_accumulation_steps, lr_fn=lr_fn)
+        self.running_loss = RunningMeter("loss")
+        self.pending = _Deferred()
+        self.n_examples = 0
+        self.global_step = restorer.global_step if restorer is not None else 0
+        self.step_fn.global_step = self.global_step
+
+    def _log_point(self, start):
+        self.pending.flush()
+        if self.running_loss.val is not None:
+            vals = D.all_gather_list(self.running_loss.val)
+            self.running_loss = RunningMeter("loss", sum(vals) / len(vals))
+            self.scalar_log("loss", self.running_loss.val, self.global_step)
+        if self.step_fn.last_grad_norm is not None:
+            self.scalar_log("grad_norm", float(self.step_fn.last_grad_norm), self.global_step)
+        tot_ex = sum(D.all_gather_list(self.n_examples))
+        ex_per_sec = int(tot_ex / (time.time() - start))
+        self.log(f"============Step {self.global_step}=============")
+        self.log(f"{tot_ex} examples trained at {ex_per_sec} ex/s")
+        self.scalar_log("perf/ex_per_s", ex_per_sec, self.global_step)
+
+    def run(self):
+        o = self.opts
+        hn_every = getattr(o, "steps_per_hard_neg", -1)
+        start = time.time()
+        self.model.train()
+        while True:
+            for batch in self.build_loader():
+                self.n_examples += batch["input_ids"].size(0)
+                before = self.step_fn.global_step
+                loss = self.step_fn(batch, None)
+                self.pending.push(self.running_loss, loss)
+                if self.step_fn.global_step == before:
+                    continue                                         # accumulation micro-step
+                self.global_step = self.step_fn.global_step
+                lrs = self.lr_fn(self.global_step)
+                if isinstance(lrs, list):
+                    self.scalar_log("xlmr_lr", lrs[0], self.global_step)
+                    lrs = lrs[-1]
+                self.scalar_log("lr", lrs, self.global_step)
+                if self.global_step % self.log_every == 0:
+                    self._log_point(start)
+                if self.global_step % o.valid_steps == 0 and self.global_step > 0:
+                    self.pending.flush()
+                    if self.validate_fn is not None:
+                        val_log = self.validate_fn(self.model)
+                        for k, v in val_log.items():
+                            self.scalar_log(k, v, self.global_step)
+                    if self.model_saver is not None:
+                        self.model_saver.save(self.model, self.global_step)
+                if self.restorer is not None:
+                    self.restorer.step()
+                if hn_every != -1 and self.global_step % hn_every == 0:
+                    if self.hard_neg_fn is not None:
+                        self.hard_neg_fn(self.model)
+                    break                                            # rebuild the loader over the new negatives
+                if self.global_step >= o.num_train_steps:
+                    break
+            if self.global_step >= o.num_train_steps:
+                break
+        self.pending.flush()
+        return self.global_step

@@ -76,9 +76,10 @@ class TrainStep(object):
             self.model._arena().word_emb_dense = False
             self.global_step += 1
             if self.lr_fn is not None:
-                lr = self.lr_fn(self.global_step)
-                for g in self.optimizer.param_groups:
-                    g["lr"] = lr
+                lr = self.lr_fn(self.global_step)              # one value, or one per parameter group
+                groups = self.optimizer.param_groups
+                for g, v in zip(groups, lr if isinstance(lr, (list, tuple)) else [lr] * len(groups)):
+                    g["lr"] = v
             if self.grad_norm != -1 and self.grad_norm > 0:
                 self.last_grad_norm = clip_grad_norm_(self.optimizer, self.grad_norm)
             self.optimizer.step()
