@@ -326,7 +326,52 @@ def case_sched():
     return out
 
 
+def case_sampling():
+    """data/mlm.py random_word, data/mrm.py _get_img_mask, data/itm.py sample_negative + the id pairs of
+    ItmRankDataset.__getitem__, all under fixed `random` seeds."""
+    import random
+    import importlib
+    cwd = os.getcwd()
+    os.chdir("/root/reference")                 # data/mlm.py reads object_labels/*.txt relative to the cwd at import
+    try:
+        mlm = importlib.import_module("data.mlm")
+        mrm = importlib.import_module("data.mrm")
+        ditm = importlib.import_module("data.itm")
+    finally:
+        os.chdir(cwd)
+    out = {}
+    lens = [1, 3, 9, 17, 40, 58]
+    random.seed(11)
+    toks, labs = [], []
+    for k, n in enumerate(lens * 3):
+        ids = [int(x) for x in cases.synth.det_randint(n, 5, 250001, 300 + k, 2)]
+        t, l = mlm.random_word(ids, (5, 250001), 250001)
+        toks += t
+        labs += l
+    out["random_word|lens"] = np.array(lens * 3)
+    out["random_word|tokens"] = np.array(toks)
+    out["random_word|labels"] = np.array(labs)
+    random.seed(12)
+    nbbs = [1, 2, 10, 36, 100, 5, 3, 64]
+    out["img_mask|nbbs"] = np.array(nbbs)
+    out["img_mask|flat"] = np.concatenate([mrm._get_img_mask(0.15, n).numpy().astype(np.uint8) for n in nbbs])
+    random.seed(13)
+    imgs = [f"img{i}" for i in range(12)]
+    txts = [f"txt{i}" for i in range(36)]
+    img2txts = {f"img{i}": [f"txt{3 * i + k}" for k in range(3)] for i in range(12)}
+    pairs = []
+    for t in (0, 7, 20, 35, 14):
+        gi = f"img{t // 3}"
+        for ns in (1, 2):
+            neg_i = ditm.sample_negative(imgs, [gi], ns)
+            neg_t = ditm.sample_negative(txts, img2txts[gi], ns)
+            pairs += [f"txt{t}|{gi}"] + [f"txt{t}|{i}" for i in neg_i] + [f"{x}|{gi}" for x in neg_t]
+    out["rank|pairs"] = np.array(pairs)
+    return out
+
+
 CASES = {
+    "sampling": case_sampling,
     "sched": case_sched,
     "loader": case_loader,
     "retrieval": case_retrieval,

@@ -595,3 +595,38 @@ def test_finetune_loop_control_flow():
     # the per-group learning rates TrainStep would install
     lrs = loop.lr_fn(3)
     assert lrs == [get_xlmr_lr_sched(3, opts)] * 2 + [get_lr_sched(3, opts)] * 2
+
+
+def test_sampling_draws_match_reference(golden):
+    """uc2_b200.sampling under the seeds of tests/golden/make_golden.py::case_sampling (the reference's own
+    random_word / _get_img_mask / sample_negative produced the fixture): same `random` stream, same draws."""
+    import random
+    from uc2_b200 import sampling as S, synth
+    g = golden("sampling")
+    lens = [int(x) for x in g["random_word|lens"]]
+    random.seed(11)
+    toks, labs = [], []
+    for k, n in enumerate(lens):
+        ids = [int(x) for x in synth.det_randint(n, 5, 250001, 300 + k, 2)]
+        t, l = S.random_word(ids, (5, 250001), 250001)
+        assert t is ids                                                   # edited in place, like the reference
+        toks += t
+        labs += l
+    np.testing.assert_array_equal(toks, g["random_word|tokens"])
+    np.testing.assert_array_equal(labs, g["random_word|labels"])
+    assert any(l != -1 for l in labs[:1])                                 # a 1-token sentence still gets its mask
+    random.seed(12)
+    flat = np.concatenate([S.get_img_mask(0.15, int(n)).numpy().astype(np.uint8) for n in g["img_mask|nbbs"]])
+    np.testing.assert_array_equal(flat, g["img_mask|flat"])
+    random.seed(13)
+    imgs = [f"img{i}" for i in range(12)]
+    txts = [f"txt{i}" for i in range(36)]
+    img2txts = {f"img{i}": [f"txt{3 * i + k}" for k in range(3)] for i in range(12)}
+    pairs = []
+    for t in (0, 7, 20, 35, 14):
+        gi = f"img{t // 3}"
+        for ns in (1, 2):
+            pairs += [f"{a}|{b}" for a, b in S.rank_id_pairs(f"txt{t}", gi, imgs, txts, img2txts[gi], ns)]
+    assert pairs == list(g["rank|pairs"])
+    ids, lab = S.create_mlm_io([7, 8, 9], (5, 100), 99, 0, 2)
+    assert ids[0] == 0 and ids[-1] == 2 and lab[0] == -1 and lab[-1] == -1 and ids.numel() == lab.numel() == 5
