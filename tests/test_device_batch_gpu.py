@@ -95,3 +95,48 @@ def test_model_consumes_device_batch():
         a = m(dc.mrfr(ids, img_idx, masks), task="mrfr", compute_loss=True)
         b = m(B.to_device(B.collate_mrfr(items, masks), "cuda"), task="mrfr", compute_loss=True)
     torch.testing.assert_close(a, b, rtol=1e-6, atol=0)
+
+
+def test_pipeline_from_stores_to_training_loop(tmp_path):
+    """TextDB + FeatureArena -> datasets -> TokenBucketSampler -> DeviceCollator -> MetaLoader -> PretrainLoop:
+    the whole caller side of the path, three tasks, two optimizer steps on a 2-layer model."""
+    import random
+    from types import SimpleNamespace
+    from uc2_b200 import datasets as DS, model
+    from uc2_b200.device_batch import DeviceCollator, FeatureArena
+    from uc2_b200.loader import MetaLoader, TokenBucketSampler
+    from uc2_b200.optim import AdamW
+    from uc2_b200.pretrain_loop import PretrainLoop
+    from uc2_b200.utils import set_dropout
+    V = cases.SMALL_VOCAB
+    imgs = cases._items(12, 41, V, "vlxlmr", bb_range=(10, 30))
+    soft = [synth.make_soft_labels(it["img_feat"].size(0), 500 + i) for i, it in enumerate(imgs)]
+    arena = FeatureArena([it["img_feat"] for it in imgs], [it["img_pos_feat"] for it in imgs], soft)
+    names = [f"img{i}" for i in range(12)]
+    caps = cases._items(36, 42, V, "vlxlmr", txt_range=(6, 20))
+    ex = {f"t{k}": {"input_ids": c["input_ids"][1:-1].tolist(), "img_fname": f"img{k // 3}"} for k, c in enumerate(caps)}
+    db = DS.TextDB(ex, mask=V - 1, v_range=(5, V - 1))
+    idx = DS.ImageIndex(arena, names)
+    dc = DeviceCollator(arena)
+    random.seed(1); np.random.seed(1)
+    dsets = {"mlm_coco": DS.MlmDataset(db, idx), "mrfr_coco": DS.MrfrDataset(0.15, db, idx),
+             "mrc-kl_coco": DS.MrcDataset(0.15, db, idx), "itm_coco": DS.ItmDataset(db, idx)}
+    loaders = {}
+    for name, d in dsets.items():
+        sampler = TokenBucketSampler(d.lens, 16, 8 * 60, droplast=True)
+        loaders[name] = DS.BatchLoader(d, sampler, lambda items, d=d: type(d).collate(dc, items))
+    b = next(iter(loaders["mrc-kl_coco"]))
+    assert b["img_feat"].is_cuda and b["label_targets"].shape[1] == 1601 and b["input_ids"].shape[0] % 8 == 0
+    cfg = cases.config(2)
+    m = model.VLXLMRForPretraining(cfg, 2048, 1601)
+    m.load_state_dict(cases.with_aliases(cases.weights(cfg, "pretrain"), "pretrain"), strict=False)
+    m.cuda().train()
+    set_dropout(m, 0.1)
+    opt = AdamW([{"params": list(m.parameters()), "weight_decay": 0.01}], lr=1e-4, betas=(0.9, 0.98))
+    opts = SimpleNamespace(gradient_accumulation_steps=1, num_train_steps=4, valid_steps=10, grad_norm=5.0,
+                           itm_ot_lambda=0.1, ot_pos_only=False, learning_rate=1e-4, decay="linear", warmup_steps=1)
+    loop = PretrainLoop(m, opt, opts, log_every=2)
+    assert loop.run(MetaLoader(loaders)) == 4
+    seen = [k for k, mt in loop.task2loss.items() if mt.val is not None]
+    assert seen and all(np.isfinite(loop.task2loss[k].val) for k in seen)
+    assert sum(loop.n_examples.values()) >= 4 * 8

@@ -630,3 +630,66 @@ def test_sampling_draws_match_reference(golden):
     assert pairs == list(g["rank|pairs"])
     ids, lab = S.create_mlm_io([7, 8, 9], (5, 100), 99, 0, 2)
     assert ids[0] == 0 and ids[-1] == 2 and lab[0] == -1 and lab[-1] == -1 and ids.numel() == lab.numel() == 5
+
+
+def test_in_memory_datasets_host_logic():
+    """uc2_b200.datasets: sample construction over a (stubbed) feature arena -- lengths for the token-bucket sampler,
+    rank sharding, masking alignment, negative sampling invariants, collate dispatch."""
+    import random
+    from uc2_b200 import datasets as DS
+    from uc2_b200.loader import TokenBucketSampler
+    n_img, cpi = 9, 3
+    class Arena(object):                       # the only two things the datasets ask of a FeatureArena
+        nbb = [10 + 7 * i for i in range(n_img)]
+        def __len__(self):
+            return n_img
+    arena = Arena()
+    names = [f"img{i}" for i in range(n_img)]
+    ex = {f"t{k}": {"input_ids": [5 + (k * 13 + j) % 200 for j in range(3 + k % 9)], "img_fname": f"img{k // cpi}"}
+          for k in range(n_img * cpi)}
+    ex["too_long"] = {"input_ids": list(range(5, 80)), "img_fname": "img0"}
+    db = DS.TextDB(ex, max_txt_len=60, mask=999, v_range=(5, 900))
+    assert "too_long" not in db.ids and len(db.ids) == 27
+    assert db.combine_inputs([7, 8]).tolist() == [0, 7, 8, 2] and db.img2txts["img2"] == ["t6", "t7", "t8"]
+    idx = DS.ImageIndex(arena, names)
+    base = DS.MrfrDataset(0.15, db, idx, rank=1, world=2)
+    assert base.ids == db.ids[1::2]
+    assert base.lens == [len(ex[i]["input_ids"]) + idx.name2nbb[ex[i]["img_fname"]] for i in base.ids]
+    random.seed(0)
+    ids, k, m = base[3]
+    assert ids[0] == 0 and ids[-1] == 2 and m.dtype == torch.bool and m.numel() == arena.nbb[k] and bool(m.any())
+    mlm = DS.MlmDataset(db, idx)
+    a, lab, k = mlm[4]
+    assert a.numel() == lab.numel() == len(ex["t4"]["input_ids"]) + 2 and lab[0] == -1 and lab[-1] == -1
+    changed = (a[1:-1] != torch.tensor(ex["t4"]["input_ids"])).nonzero().squeeze(1) + 1
+    assert bool((lab[changed] != -1).all()) and bool((lab != -1).any()) and k == 1
+    assert ex["t4"]["input_ids"] == [5 + (4 * 13 + j) % 200 for j in range(7)]      # the store itself is untouched
+    # ITM: labels, negatives and lens move together and are reproducible under the seeds
+    np.random.seed(3); random.seed(3)
+    itm = DS.ItmDataset(db, idx, neg_sample_p=0.5)
+    for i, id_ in enumerate(itm.ids):
+        own = ex[id_]["img_fname"]
+        assert (itm.train_imgs[i] == own) == (itm.labels[i] == 1)
+        assert itm.lens[i] == len(ex[id_]["input_ids"]) + idx.name2nbb[itm.train_imgs[i]]
+    snap = (list(itm.labels), list(itm.train_imgs))
+    np.random.seed(3); random.seed(3)
+    itm.new_epoch()
+    assert (list(itm.labels), list(itm.train_imgs)) == snap and 0 < sum(snap[0]) < 27
+    batches = list(iter(TokenBucketSampler(itm.lens, 8, 1000, droplast=False)))
+    assert sorted(i for b in batches for i in b) == list(range(27))
+    # rank items: positive first, wrong images, then captions of other images
+    rk = DS.ItmRankDataset(db, idx, neg_sample_size=2)
+    item = rk[5]
+    assert len(item) == 5 and item[0][1] == 1
+    assert all(k != 1 for _, k in item[1:3]) and all(k == 1 for _, k in item[3:])
+    own_caps = [db.combine_inputs(ex[t]["input_ids"]).tolist() for t in ("t3", "t4", "t5")]
+    assert item[0][0].tolist() == own_caps[2] and all(p[0].tolist() not in own_caps for p in item[3:])
+
+    class Rec(object):
+        def __getattr__(self, name):
+            return lambda *a, **k: (name, a, k)
+    name, args, _ = rk.collate(Rec(), [item, rk[6]])
+    assert name == "itm_rank" and len(args[0]) == 10 and args[2] == 5
+    name, args, kw = DS.ItmDataset.collate(Rec(), [itm[0], itm[1]], with_ot=False)
+    assert name == "itm" and args[2] == [int(itm.labels[0]), int(itm.labels[1])] and kw == {"with_ot": False}
+    assert DS.MrcDataset.collate(Rec(), [base[0]])[0] == "mrc" and DS.MlmDataset.collate(Rec(), [mlm[0]])[0] == "mlm"
