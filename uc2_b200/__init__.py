@@ -9,6 +9,7 @@ Modules, named after what they replace in the reference tree:
     batch, loader       data/*.py collates, data/sampler.py, data/loader.py
     sampling            token / region masking and negative sampling draws (data/mlm.py, data/mrm.py, data/itm.py)
     device_batch        the same collates built on the device from an HBM-resident feature arena
+    datasets            in-memory task datasets over that arena (data/itm.py, data/mlm.py, data/mrm.py item logic)
     retrieval           itm.py evaluate / inference / validate / get_hard_negs, eval/itm.py
     train, pretrain_loop, validate      the loops of pretrain.py and itm.py
     save, utils         utils/save.py, utils/misc.py
