@@ -693,3 +693,13 @@ def test_in_memory_datasets_host_logic():
     name, args, kw = DS.ItmDataset.collate(Rec(), [itm[0], itm[1]], with_ot=False)
     assert name == "itm" and args[2] == [int(itm.labels[0]), int(itm.labels[1])] and kw == {"with_ot": False}
     assert DS.MrcDataset.collate(Rec(), [base[0]])[0] == "mrc" and DS.MlmDataset.collate(Rec(), [mlm[0]])[0] == "mlm"
+
+
+def test_checkpoint_dict_helpers():
+    from uc2_b200.save import inject_early_adaptation, rename_checkpoint
+    ck = {"embeddings.word_embeddings.weight": 1, "encoder.layer.0.output.dense.bias": 2}
+    assert rename_checkpoint(ck) is ck and sorted(ck) == ["bert.embeddings.word_embeddings.weight",
+                                                          "bert.encoder.layer.0.output.dense.bias"]
+    w, b = torch.ones(768, 2048), torch.zeros(768)
+    out = inject_early_adaptation({}, {"v2w_linear.weight": w, "v2w_linear.bias": b})
+    assert out["roberta.img_embeddings.img_linear.weight"] is w and out["roberta.img_embeddings.img_linear.bias"] is b

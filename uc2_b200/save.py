@@ -63,3 +63,18 @@ class TrainingRestorer(object):
         self.model.load_state_dict(checkpoint["model_state_dict"], strict=False)
         self.model._arena()                   # refresh the bf16 shadows from the loaded masters
         self.optimizer.load_state_dict(checkpoint["optim_state_dict"])
+
+
+def rename_checkpoint(checkpoint, add_prefix="bert."):
+    """pretrain.py:72-80 (--rename_checkpoints): prefix every key of a checkpoint dict, in place."""
+    for key in list(checkpoint):
+        checkpoint[add_prefix + key] = checkpoint.pop(key)
+    return checkpoint
+
+
+def inject_early_adaptation(checkpoint, early_adaptation_checkpoint, prefix="roberta."):
+    """pretrain.py:438-441 (--early_adaptation): the visual-to-word projection learnt in the early-adaptation stage
+    becomes the image embedding's input projection."""
+    checkpoint[prefix + "img_embeddings.img_linear.weight"] = early_adaptation_checkpoint["v2w_linear.weight"]
+    checkpoint[prefix + "img_embeddings.img_linear.bias"] = early_adaptation_checkpoint["v2w_linear.bias"]
+    return checkpoint
