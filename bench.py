@@ -177,7 +177,18 @@ class Clocks(threading.Thread):
 # --------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference step on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, workload, n_pairs=12):
+def cpu_dropout_masks(b, p, layers, hidden=768, heads=12):
+    """Dropout multipliers for the oracle (its `drop=` argument) drawn like nn.Dropout in training mode: the
+    reference trains with hidden / attention dropout p (config/uc2-base.json), so its CPU step pays for them too."""
+    if p <= 0:
+        return None
+    B, T, R, S = b["input_ids"].size(0), b["input_ids"].size(1), b["img_feat"].size(1), b["attn_masks"].size(1)
+    mk = lambda *shape: torch.bernoulli(torch.full(shape, 1.0 - p)) / (1.0 - p)
+    return {"emb": mk(B, T + R, hidden),
+            "layers": [(mk(B, heads, S, S), mk(B, S, hidden), mk(B, S, hidden)) for _ in range(layers)]}
+
+
+def cpu_reference_steps(steps, warmup, workload, n_pairs=12, dropout=0.1):
     from oracle import uc2_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = UC2Config()
@@ -197,10 +208,11 @@ def cpu_reference_steps(steps, warmup, workload, n_pairs=12):
         task, b = batches[(step - 1) % len(batches)]
         for p in sd.values():
             p.grad = None
+        drop = cpu_dropout_masks(b, dropout, cfg.num_hidden_layers)
         if task == "rank":
-            loss = O.forward_retrieval(sd, fam, b).mean()
+            loss = O.forward_retrieval(sd, fam, b, drop=drop).mean()
         else:
-            loss = O.pretraining_loss(O.forward_pretraining(sd, fam, b, task), task)
+            loss = O.pretraining_loss(O.forward_pretraining(sd, fam, b, task, drop=drop), task)
         loss.backward()
         with torch.no_grad():
             names = [k for k, p in sd.items() if p.grad is not None]
@@ -384,10 +396,11 @@ def main():
                         e2e={"value": val, "unit": "pair-scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
             print(json.dumps(line))
             return
-        val, ms, n = cpu_reference_steps(steps, warm, args.workload)
+        val, ms, n = cpu_reference_steps(steps, warm, args.workload, dropout=args.dropout)
         line = dict(base, impl="reference", value=val, ms_per_step=ms, dtype="f32", steps=steps, warmup=warm,
                     cpu_baseline={"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                                  "sample": f"{n} pairs per step (oracle port of the reference step, fp32, all host threads)"},
+                                  "sample": f"{n} pairs per step (oracle port of the reference step incl. dropout "
+                                            f"{args.dropout}, fp32, all host threads)"},
                     e2e={"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         print(json.dumps(line))
         return
@@ -559,11 +572,11 @@ def main():
     if hbm_store is not None:
         line["e2e_hbm_feature_store"] = hbm_store
     if world == 1 and not args.no_cpu_baseline:
-        val, ms, n = cpu_reference_steps(6, 1, args.workload)
+        val, ms, n = cpu_reference_steps(6, 1, args.workload, dropout=args.dropout)
         line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                 "ms_per_step": ms,
                                 "sample": f"{n} pairs per step, 6 timed steps after 1 warm-up (oracle port of the reference "
-                                          "step: forward, loss, backward, clip, AdamW; fp32, all host threads, p_dropout 0)"}
+                                          f"step: forward, loss, backward, clip, AdamW; fp32, all host threads, dropout {args.dropout})"}
     print(json.dumps(line), flush=True)
 
 

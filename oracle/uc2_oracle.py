@@ -307,7 +307,8 @@ def optimal_transport_dist(txt_emb, img_emb, txt_pad, img_pad, beta=0.5, iterati
 # ----------------------------------------------------------------------------
 # task forwards (model/model.py:495-775, model/itm.py:28-55)
 # ----------------------------------------------------------------------------
-def forward_pretraining(sd, fam, batch, task, compute_loss=True, ot_pos_only=False):
+def forward_pretraining(sd, fam, batch, task, compute_loss=True, ot_pos_only=False, drop=None):
+    """drop: optional dropout multipliers for the encoder (see encoder()); the heads have no dropout."""
     ids = batch["input_ids"]
     pos = batch.get("position_ids") if (task == "tlm" or fam.name != "vlxlmr") else None
     feat, posf = batch.get("img_feat"), batch.get("img_pos_feat")
@@ -315,28 +316,28 @@ def forward_pretraining(sd, fam, batch, task, compute_loss=True, ot_pos_only=Fal
     if task in ("mlm", "tlm", "tlm-ni"):
         if task == "tlm-ni":
             feat = posf = gi = None
-        h = encoder(sd, fam, ids, pos, feat, posf, am, gi)
+        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, drop=drop)
         h = h[:, :ids.size(1)]                                   # model.py:583
         lab = batch["txt_labels"]
         scores = mlm_head(sd, fam, masked_hidden(h, lab != -1))
         return F.cross_entropy(scores, lab[lab != -1], reduction="none") if compute_loss else scores
     if task in ("mmxlm", "vmlm"):                                 # model.py:598-624
-        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"])
+        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"], drop=drop)
         lab = batch["txt_labels"]
         scores = mlm_head(sd, fam, masked_hidden(h, lab != -1))
         return F.cross_entropy(scores, lab[lab != -1], reduction="none") if compute_loss else scores
     if task in ("mmxlm-soft", "vmlm-soft"):                       # model.py:626-651
-        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"])
+        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"], drop=drop)
         pred = mlm_head(sd, fam, masked_hidden(h, batch["tgt_masks"]))[:, torch.as_tensor(batch["valid_token_ids"])]
         if not compute_loss:
             return pred
         return F.kl_div(F.log_softmax(pred, -1), batch["label_targets"], reduction="none")
     if task == "mrfr":
-        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"])
+        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"], drop=drop)
         pred = mrfr_head(sd, fam, masked_hidden(h, batch["img_mask_tgt"]))
         return F.mse_loss(pred, batch["feat_targets"], reduction="none") if compute_loss else pred
     if task.startswith("mrc"):
-        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"])
+        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, batch["img_masks"], drop=drop)
         pred = mrc_head(sd, masked_hidden(h, batch["img_mask_tgt"]))
         if not compute_loss:
             return pred
@@ -345,7 +346,7 @@ def forward_pretraining(sd, fam, batch, task, compute_loss=True, ot_pos_only=Fal
         tgt = batch["label_targets"][:, 1:].max(-1)[1] + 1
         return F.cross_entropy(pred, tgt, ignore_index=0, reduction="none")
     if task == "itm":
-        h = encoder(sd, fam, ids, pos, feat, posf, am, gi)
+        h = encoder(sd, fam, ids, pos, feat, posf, am, gi, drop=drop)
         scores = F.linear(pooler(sd, fam, h), sd["itm_output.weight"], sd["itm_output.bias"])
         targets = batch["targets"]
         ot = batch.get("ot_inputs")
@@ -382,7 +383,7 @@ def forward_retrieval(sd, fam, batch, compute_loss=True, margin=0.2, drop=None):
     """model/itm.py:28-55."""
     pos = None if fam.name == "vlxlmr" else batch.get("position_ids")
     h = encoder(sd, fam, batch["input_ids"], pos, batch["img_feat"], batch["img_pos_feat"],
-                batch["attn_masks"], batch["gather_index"])
+                batch["attn_masks"], batch["gather_index"], drop=drop)
     scores = F.linear(pooler(sd, fam, h), sd["rank_output.weight"], sd["rank_output.bias"])
     if not compute_loss:
         return scores
