@@ -703,3 +703,20 @@ def test_checkpoint_dict_helpers():
     w, b = torch.ones(768, 2048), torch.zeros(768)
     out = inject_early_adaptation({}, {"v2w_linear.weight": w, "v2w_linear.bias": b})
     assert out["roberta.img_embeddings.img_linear.weight"] is w and out["roberta.img_embeddings.img_linear.bias"] is b
+
+
+def test_fp16_compressed_checkpoint_loads():
+    """utils/save.py:147-162 stores restore.pt with every float tensor in fp16: such a state dict must load into the
+    fp32 parameters (the optimizer moments are cast the same way on the device)."""
+    from uc2_b200 import itm
+    from uc2_b200.save import _to_cpu
+    cfg = cases.config(1)
+    sd = cases.weights(cfg, "retrieval")
+    packed = _to_cpu({"a": sd, "n": 3, "l": [torch.ones(2), torch.arange(3)]}, half=True)
+    assert packed["a"]["rank_output.weight"].dtype == torch.float16 and packed["l"][1].dtype == torch.int64
+    assert packed["n"] == 3 and _to_cpu(sd)["rank_output.weight"].dtype == torch.float32
+    m = itm.VLXLMRForImageTextRetrieval(cfg, 2048)
+    m.load_state_dict(packed["a"], strict=False)
+    p = dict(m.named_parameters())["rank_output.weight"]
+    assert p.dtype == torch.float32
+    torch.testing.assert_close(p.detach(), sd["rank_output.weight"].half().float())

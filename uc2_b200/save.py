@@ -9,13 +9,17 @@ from os.path import exists, join
 import torch
 
 
-def _to_cpu(state):
+def _to_cpu(state, half=False):
+    """Host copy of a (nested) state.  half=True reproduces the reference's restore.pt compression
+    (utils/save.py:147-162: every float tensor stored as fp16); the default keeps fp32 so a resume is exact.
+    Either form loads: parameters and optimizer moments are cast back to fp32 on load."""
     if isinstance(state, torch.Tensor):
-        return state.detach().cpu()
+        t = state.detach().cpu()
+        return t.half() if half and t.dtype == torch.float32 else t
     if isinstance(state, dict):
-        return {k: _to_cpu(v) for k, v in state.items()}
+        return {k: _to_cpu(v, half) for k, v in state.items()}
     if isinstance(state, (list, tuple)):
-        return type(state)(_to_cpu(v) for v in state)
+        return type(state)(_to_cpu(v, half) for v in state)
     return state
 
 
@@ -32,7 +36,8 @@ class ModelSaver(object):
 
 
 class TrainingRestorer(object):
-    def __init__(self, output_dir, model, optimizer, save_steps=1000):
+    def __init__(self, output_dir, model, optimizer, save_steps=1000, fp16_compress=False):
+        self.fp16_compress = fp16_compress
         self.save_path = join(output_dir, "restore.pt")
         self.backup_path = join(output_dir, "restore_backup.pt")
         self.output_dir = output_dir
@@ -48,8 +53,9 @@ class TrainingRestorer(object):
 
     def save(self):
         os.makedirs(self.output_dir, exist_ok=True)
-        checkpoint = {"global_step": self.global_step, "model_state_dict": _to_cpu(self.model.state_dict()),
-                      "optim_state_dict": _to_cpu(self.optimizer.state_dict())}
+        checkpoint = {"global_step": self.global_step,
+                      "model_state_dict": _to_cpu(self.model.state_dict(), self.fp16_compress),
+                      "optim_state_dict": _to_cpu(self.optimizer.state_dict(), self.fp16_compress)}
         if exists(self.save_path):           # keep the previous one in case this write is interrupted
             os.replace(self.save_path, self.backup_path)
         torch.save(checkpoint, self.save_path)
