@@ -164,3 +164,34 @@ def test_adamw(golden):
         for n, p, gr, m, v in zip(names, ps, gs, ms, vs):
             O.adamw_step(p, gr, m, v, step, lr, 0.9, 0.98, 1e-6, 0.0 if O.no_decay(n) else 0.01)
             np.testing.assert_allclose(p.numpy(), g[f"p{step}|{n}"], rtol=1e-5, atol=1e-7)
+
+
+def test_dropout_multipliers_reach_every_task_forward():
+    """The oracle's `drop=` multipliers (the explicit stand-in for nn.Dropout in training mode) thread through the
+    task forwards: all-ones masks reproduce the no-dropout result exactly, real masks change it, and the scaling of a
+    kept element is 1 / (1 - p)."""
+    cfg = cases.config(1)
+    fam = O.Family("vlxlmr")
+    sd = cases.weights(cfg, "pretrain")
+    b = cases.batch_mrfr()
+    B_, T, R, S = b["input_ids"].size(0), b["input_ids"].size(1), b["img_feat"].size(1), b["attn_masks"].size(1)
+    ones = {"emb": torch.ones(B_, T + R, 768), "layers": [(torch.ones(B_, 12, S, S), torch.ones(B_, S, 768),
+                                                           torch.ones(B_, S, 768))]}
+    base = O.forward_pretraining(sd, fam, b, "mrfr")
+    same = O.forward_pretraining(sd, fam, b, "mrfr", drop=ones)
+    assert torch.equal(base, same)
+    g = torch.Generator().manual_seed(0)
+    p = 0.1
+    mk = lambda *s: torch.bernoulli(torch.full(s, 1 - p), generator=g) / (1 - p)
+    real = {"emb": mk(B_, T + R, 768), "layers": [(mk(B_, 12, S, S), mk(B_, S, 768), mk(B_, S, 768))]}
+    vals = real["emb"].unique().tolist()
+    assert len(vals) == 2 and vals[0] == 0.0 and abs(vals[1] - 1 / (1 - p)) < 1e-6
+    diff = O.forward_pretraining(sd, fam, b, "mrfr", drop=real)
+    assert not torch.allclose(base, diff)
+    rsd = cases.weights(cfg, "retrieval")
+    rb = cases.batch_rank()
+    S2 = rb["attn_masks"].size(1)
+    n = rb["input_ids"].size(0)
+    ones2 = {"emb": torch.ones(n, rb["input_ids"].size(1) + rb["img_feat"].size(1), 768),
+             "layers": [(torch.ones(n, 12, S2, S2), torch.ones(n, S2, 768), torch.ones(n, S2, 768))]}
+    assert torch.equal(O.forward_retrieval(rsd, fam, rb), O.forward_retrieval(rsd, fam, rb, drop=ones2))
