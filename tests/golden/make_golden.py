@@ -326,6 +326,83 @@ def case_sched():
     return out
 
 
+def _digest(t):
+    """Small fingerprint of a float tensor: shape, per-sample sums (fp64) and 64 strided samples."""
+    f = t.detach().double()
+    flat = f.reshape(-1)
+    idx = torch.linspace(0, flat.numel() - 1, 64).long()
+    return np.concatenate([np.array(f.shape, dtype=np.float64), f.reshape(f.size(0), -1).sum(1).numpy(),
+                           flat[idx].numpy()])
+
+
+def _dump_batch(out, tag, batch):
+    for k, v in batch.items():
+        if isinstance(v, dict):
+            _dump_batch(out, f"{tag}|{k}", v)
+        elif torch.is_tensor(v):
+            out[f"{tag}|{k}"] = _digest(v) if v.is_floating_point() else v.numpy().astype(np.int64)
+        else:
+            out[f"{tag}|{k}"] = np.array([v])
+
+
+def case_collate():
+    """The reference's WHOLE collate functions (data/itm.py, data/mrm.py, data/mlm.py) on the deterministic items of
+    tests/cases.py: integer / mask outputs stored in full, float tensors as digests."""
+    import importlib
+    cwd = os.getcwd()
+    os.chdir("/root/reference")
+    try:
+        mlm = importlib.import_module("data.mlm")
+        mrm = importlib.import_module("data.mrm")
+        ditm = importlib.import_module("data.itm")
+    finally:
+        os.chdir(cwd)
+    out = {}
+    items = cases._items(6, 71, cases.SMALL_VOCAB, "vlxlmr")
+    ones = lambda it: torch.ones(it["input_ids"].numel() + it["img_feat"].size(0), dtype=torch.long)
+    targets = [1, 0, 0, 1, 1, 0]
+    _dump_batch(out, "itm_ot", ditm.xlmr_itm_ot_collate(
+        [(it["input_ids"], it["img_feat"], it["img_pos_feat"], ones(it), torch.tensor([t]))
+         for it, t in zip(items, targets)]))
+    _dump_batch(out, "itm", ditm.xlmr_itm_collate(
+        [(it["input_ids"], it["img_feat"], it["img_pos_feat"], ones(it), torch.tensor([t]))
+         for it, t in zip(items, targets)]))
+    _dump_batch(out, "rank", ditm.xlmr_itm_rank_collate(
+        [[(it["input_ids"], it["img_feat"], it["img_pos_feat"], ones(it)) for it in items]]))
+    lab = cases.synth.make_mlm_labels([it["input_ids"] for it in items], 71, mask_id=cases.SMALL_VOCAB - 1,
+                                      vocab=cases.SMALL_VOCAB)
+    _dump_batch(out, "mlm", mlm.xlmr_mlm_collate(
+        [(m, it["img_feat"], it["img_pos_feat"], ones(it), l) for it, (m, l) in zip(items, lab)]))
+    nbbs = [it["img_feat"].size(0) for it in items]
+    masks = cases.synth.make_img_masks(nbbs, 71)
+    tgt = [mrm._get_img_tgt_mask(mk, it["input_ids"].numel()) for mk, it in zip(masks, items)]
+    _dump_batch(out, "mrfr", mrm.xlmr_mrfr_collate(
+        [(it["input_ids"], it["img_feat"], it["img_pos_feat"], ones(it), mk, tg)
+         for it, mk, tg in zip(items, masks, tgt)]))
+    # VTLM with images (co-masking datasets): per-sample position ids travel through the collate
+    from uc2_b200.batch import tlm_position_ids
+    _dump_batch(out, "tlm", mlm.xlmr_mlm_dmasking_collate(
+        [(m, it["img_feat"], it["img_pos_feat"], ones(it), l, tlm_position_ids(m)) for it, (m, l) in zip(items, lab)]))
+    # MRTM: hard token labels over the packed sequence / soft token distributions of the masked regions
+    img_lab = []
+    for i, (nb, mk) in enumerate(zip(nbbs, masks)):
+        tok = torch.from_numpy(cases.synth.det_randint(nb, 5, cases.SMALL_VOCAB, 71 * 77 + i, 5).astype(np.int64))
+        img_lab.append(torch.where(mk, tok, torch.full_like(tok, -1)))
+    _dump_batch(out, "mmxlm", mlm.xlmr_mmxlm_collate(
+        [(m, it["img_feat"], it["img_pos_feat"], ones(it), mk, torch.cat([l, il]))
+         for it, (m, l), mk, il in zip(items, lab, masks, img_lab)]))
+    tok_soft = [torch.softmax(torch.from_numpy(cases.synth.det_normal((nb, 16), 71 * 5 + i, 2.0)).float(), -1)
+                for i, nb in enumerate(nbbs)]
+    _dump_batch(out, "mmxlm_soft", mlm.xlmr_mmxlm_softlabel_collate(
+        [(it["input_ids"], it["img_feat"], it["img_pos_feat"], ones(it), mk, tg, ts)
+         for it, mk, tg, ts in zip(items, masks, tgt, tok_soft)]))
+    soft = [cases.synth.make_soft_labels(nb, 71 * 31 + i) for i, nb in enumerate(nbbs)]
+    _dump_batch(out, "mrc", mrm.xlmr_mrc_collate(
+        [(it["input_ids"], it["img_feat"], it["img_pos_feat"], sl, ones(it), mk, tg)
+         for it, sl, mk, tg in zip(items, soft, masks, tgt)]))
+    return out
+
+
 def case_sampling():
     """data/mlm.py random_word, data/mrm.py _get_img_mask, data/itm.py sample_negative + the id pairs of
     ItmRankDataset.__getitem__, all under fixed `random` seeds."""
@@ -371,6 +448,7 @@ def case_sampling():
 
 
 CASES = {
+    "collate": case_collate,
     "sampling": case_sampling,
     "sched": case_sched,
     "loader": case_loader,

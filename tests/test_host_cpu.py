@@ -720,3 +720,62 @@ def test_fp16_compressed_checkpoint_loads():
     p = dict(m.named_parameters())["rank_output.weight"]
     assert p.dtype == torch.float32
     torch.testing.assert_close(p.detach(), sd["rank_output.weight"].half().float())
+
+
+def _digest(t):
+    f = t.detach().double()
+    flat = f.reshape(-1)
+    idx = torch.linspace(0, flat.numel() - 1, 64).long()
+    return np.concatenate([np.array(f.shape, dtype=np.float64), f.reshape(f.size(0), -1).sum(1).numpy(), flat[idx].numpy()])
+
+
+def _check_batch(g, tag, batch, skip=()):
+    keys = [k for k in g.files if k.startswith(tag + "|")]
+    assert keys
+    for k in keys:
+        path = k.split("|")[1:]
+        if path[0] in skip:
+            continue
+        v = batch
+        for p in path:
+            v = v[p]
+        if torch.is_tensor(v):
+            if v.is_floating_point():
+                np.testing.assert_allclose(_digest(v), g[k], rtol=0, atol=0, err_msg=k)
+            else:
+                np.testing.assert_array_equal(v.numpy().astype(np.int64), g[k], err_msg=k)
+        else:
+            assert v == g[k][0], k
+    ours = set(batch) - {"n_masked"}
+    theirs = {k.split("|")[1] for k in keys}
+    assert ours == theirs, (tag, ours ^ theirs)
+
+
+def test_whole_collates_match_reference(golden):
+    """uc2_b200.batch.collate_* against the reference's complete collate functions (tests/golden/collate.npz was
+    written by data/itm.py, data/mrm.py and data/mlm.py themselves): every key, integer tensors bit-exact, float
+    tensors by digest (shape, per-sample sums, strided samples), masks as 0/1."""
+    from uc2_b200 import batch as B, synth
+    g = golden("collate")
+    items = cases._items(6, 71, cases.SMALL_VOCAB, "vlxlmr")
+    targets = [1, 0, 0, 1, 1, 0]
+    _check_batch(g, "itm_ot", B.collate_itm(items, targets, with_ot=True))
+    _check_batch(g, "itm", B.collate_itm(items, targets, with_ot=False))
+    _check_batch(g, "rank", B.collate_itm_rank(items, 6))
+    lab = synth.make_mlm_labels([it["input_ids"] for it in items], 71, mask_id=cases.SMALL_VOCAB - 1,
+                                vocab=cases.SMALL_VOCAB)
+    _check_batch(g, "mlm", B.collate_mlm(items, lab))
+    nbbs = [it["img_feat"].size(0) for it in items]
+    masks = synth.make_img_masks(nbbs, 71)
+    _check_batch(g, "mrfr", B.collate_mrfr(items, masks))
+    soft = [synth.make_soft_labels(nb, 71 * 31 + i) for i, nb in enumerate(nbbs)]
+    _check_batch(g, "mrc", B.collate_mrc(items, masks, soft))
+    _check_batch(g, "tlm", B.collate_tlm(items, lab))
+    img_lab = []
+    for i, (nb, mk) in enumerate(zip(nbbs, masks)):
+        tok = torch.from_numpy(synth.det_randint(nb, 5, cases.SMALL_VOCAB, 71 * 77 + i, 5).astype(np.int64))
+        img_lab.append(torch.where(mk, tok, torch.full_like(tok, -1)))
+    _check_batch(g, "mmxlm", B.collate_mmxlm(items, lab, masks, img_lab))
+    tok_soft = [torch.softmax(torch.from_numpy(synth.det_normal((nb, 16), 71 * 5 + i, 2.0)).float(), -1)
+                for i, nb in enumerate(nbbs)]
+    _check_batch(g, "mmxlm_soft", B.collate_mmxlm_soft(items, masks, tok_soft))

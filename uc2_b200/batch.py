@@ -109,7 +109,9 @@ def tlm_position_ids(input_ids, start=2):
 
 
 def collate_tlm(items, labeled, pad_id=1):
-    """xlmr_tlm_ni_dmasking_collate (data/mlm.py:803-842): as collate_mlm plus per-sample position ids padded with 1."""
+    """xlmr_mlm_dmasking_collate (data/mlm.py:845-884): as collate_mlm plus per-sample position ids padded with 1.
+    (The text-only sibling xlmr_tlm_ni_dmasking_collate, 803-842, differs only in gather_index = None; run it as task
+    'tlm-ni', which ignores the image side.)"""
     batch = collate_mlm(items, labeled, pad_id)
     batch["position_ids"] = pad_sequence([tlm_position_ids(m) for m, _ in labeled], batch_first=True, padding_value=1)
     return batch
