@@ -2,7 +2,6 @@
 C-ABI, against a plain torch fp32 layer_norm (FusedLayerNorm call sites of model/layer.py:108,149,196,242).
 The dropout form also returns the masked, rescaled gradient of the dense branch; its mask is checked against the
 host mirror of the counter hash (uc2_b200/dropout.py)."""
-import numpy as np
 import pytest
 import torch
 

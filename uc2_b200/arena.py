@@ -7,7 +7,6 @@ fp32 gradient arena (allreduce buckets are plain slices, no copy in/out) and the
 are a parallel bf16 shadow arena refreshed by the fused AdamW kernel.  Module parameter names and
 shapes are untouched, so state_dict()/load_state_dict()/named_parameters() behave like the reference.
 """
-import ctypes as C
 
 import torch
 

@@ -10,7 +10,6 @@ remaining backward kernels.  Semantics: mean over ranks (Horovod's default ``ave
 ``rescale_denom=1``; SURVEY 8c notes this is unpinned in the reference).
 """
 import os
-import pickle
 
 import torch
 import torch.distributed as dist

@@ -11,9 +11,7 @@ called); all arithmetic runs in the sm_100a kernels of libuc2_b200.so through uc
 There is no CPU path: inputs must live on a CUDA device.
 """
 import copy
-import ctypes as C
 import logging
-import warnings
 import weakref
 from collections import defaultdict
 

@@ -9,7 +9,6 @@ import torch
 
 from . import _lib
 from ._lib import call, stream
-from .arena import ParamArena
 
 CHUNK = 8192
 

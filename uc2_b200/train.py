@@ -8,7 +8,6 @@ Differences from the reference that are deliberate: no per-step pickled all-gath
 (pretrain.py:517 -- every rank derives the same task from the step number), no .item() host syncs per
 micro-step, bf16 + fp32 masters instead of apex O2 loss scaling.
 """
-import torch
 
 from . import distributed as D
 from .optim import clip_grad_norm_
