@@ -88,6 +88,7 @@ _SIGS = {
     "uc2_layernorm_bwd_dropout": [P, I, P, P, F, P, P, P, P, LL, P, C.c_uint, C.c_uint, F, P],
     "uc2_attention_fwd_dropout": [P, P, P, P, I, I, C.c_uint, C.c_uint, F, P],
     "uc2_attention_bwd_dropout": [P, P, P, P, P, P, P, I, I, C.c_uint, C.c_uint, F, P],
+    "uc2_attention_fwd_tc": [P, P, P, P, I, I, C.c_uint, C.c_uint, F, P],
     "uc2_encoder_fwd_dropout": [P, P, P, I, I, I, C.POINTER(LayerWeights), C.POINTER(LayerActs), I, C.POINTER(Dropout),
                                 P, SZ, P],
     "uc2_encoder_bwd_dropout": [P, P, I, I, I, C.POINTER(LayerWeights), C.POINTER(LayerActs), C.POINTER(LayerGrads),
@@ -122,7 +123,7 @@ _SIGS = {
     "uc2_grad_sqnorm": [P, P, I, P, P, P],
     "uc2_adamw_step": [P, P, P, P, P, P, I, P, P, C.POINTER(AdamwHyper), P, P],
 }
-EXPORTS = sorted(list(_SIGS) + ["uc2_last_error", "uc2_version", "uc2_launch_count",
+EXPORTS = sorted(list(_SIGS) + ["uc2_last_error", "uc2_version", "uc2_launch_count", "uc2_attention_tc_enable",
                                 "uc2_encoder_bwd_workspace_bytes", "uc2_encoder_fwd_workspace_bytes"])
 
 
@@ -140,6 +141,8 @@ def lib():
         L.uc2_encoder_bwd_workspace_bytes.argtypes = [I, I]
         L.uc2_encoder_fwd_workspace_bytes.restype = SZ
         L.uc2_encoder_fwd_workspace_bytes.argtypes = [I, I]
+        L.uc2_attention_tc_enable.restype = I
+        L.uc2_attention_tc_enable.argtypes = [I]
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.argtypes = sig
