@@ -199,9 +199,15 @@ UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long long* attn_mas
  * cores and accumulators in TMEM, S <= 160 (UC2_ERR_UNSUPPORTED above).  Same arguments and, by construction, the
  * same results (mask, dropout stream, lse) as uc2_attention_fwd_dropout, so uc2_attention_bwd* pairs with it; ctx
  * must be 32-byte aligned.  uc2_attention_tc_enable(1) (or UC2_ATTN_TCGEN05=1 in the environment) makes
- * uc2_attention_fwd / _fwd_dropout / uc2_encoder_fwd* route eligible shapes here; returns the previous setting. */
+ * the public entry points (uc2_attention_fwd*, _bwd*, uc2_encoder_fwd*, _bwd*) route eligible shapes to the _tc
+ * kernels; it returns the previous setting. */
 UC2_API int uc2_attention_fwd_tc(const void* qkv, const long long* attn_mask, void* ctx, float* lse, int B, int S,
                                  unsigned int drop_key, unsigned int drop_thresh, float drop_scale, void* stream);
+/* ... and the backward (dqkv fully overwritten for the B*S rows; delta = rowsum(dO * O) is computed inside, so
+ * there is no workspace argument).  dqkv must be 32-byte aligned. */
+UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* attn_mask, const void* ctx, const void* dctx,
+                                 const float* lse, void* dqkv, int B, int S, unsigned int drop_key,
+                                 unsigned int drop_thresh, float drop_scale, void* stream);
 UC2_API int uc2_attention_tc_enable(int on);
 
 /* ---------------------------------------------------------------------------------------------

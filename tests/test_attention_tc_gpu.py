@@ -98,3 +98,85 @@ def test_tc_rejects_long_sequences():
     rc = lib().uc2_attention_fwd_tc(qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, 0, 0, 1.0,
                                     stream())
     assert rc != 0
+
+
+def _ref_bwd(qkv, mask, dctx, B, S):
+    x = qkv.float().view(B, S, 3, 12, 64).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+    sc = x[0] @ x[1].transpose(-1, -2) / 8 + (1 - mask.float())[:, None, None, :] * -10000.0
+    o = (sc.softmax(-1) @ x[2]).permute(0, 2, 1, 3).reshape(B * S, 768)
+    o.backward(dctx.float())
+    return x.grad.permute(1, 3, 0, 2, 4).reshape(B * S, 2304)
+
+
+def _run_bwd(name, qkv, mask, ctx, dctx, lse, B, S, drop):
+    from uc2_b200._lib import call, stream
+    dqkv = torch.full((B * S, 2304), float("nan"), dtype=torch.bfloat16, device="cuda")
+    if name == "uc2_attention_bwd_tc":
+        call(name, qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+             B, S, *drop, stream())
+    else:
+        delta = torch.empty(B, 12, S, device="cuda")
+        call(name, qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+             dqkv.data_ptr(), B, S, *drop, stream())
+    torch.cuda.synchronize()
+    return dqkv
+
+
+@pytest.mark.parametrize("B,S,kind", SHAPES)
+def test_tc_backward_matches_reference_and_mma_sync(B, S, kind):
+    qkv, mask = _inputs(B, S, kind)
+    dctx = torch.randn(B * S, 768, device="cuda").bfloat16()
+    ctx, lse = _run("uc2_attention_fwd_dropout", qkv, mask, B, S, (0, 0, 1.0))
+    dqkv = _run_bwd("uc2_attention_bwd_tc", qkv, mask, ctx, dctx, lse, B, S, (0, 0, 1.0))
+    g = _ref_bwd(qkv, mask, dctx, B, S)
+    assert torch.isfinite(dqkv.float()).all()
+    scale = g.abs().max().item()
+    assert (dqkv.float() - g).abs().max().item() <= 1.5e-2 * scale     # the bar of tests/test_attention_gpu.py
+    d0 = _run_bwd("uc2_attention_bwd_dropout", qkv, mask, ctx, dctx, lse, B, S, (0, 0, 1.0))
+    assert (dqkv.float() - d0.float()).abs().max().item() <= 1.5e-2 * scale
+
+
+@pytest.mark.parametrize("B,S,kind", [(6, 160, "prefix"), (3, 77, "random"), (4, 150, "prefix")])
+def test_tc_backward_dropout_stream_is_the_mma_sync_one(B, S, kind):
+    qkv, mask = _inputs(B, S, kind)
+    dctx = torch.randn(B * S, 768, device="cuda").bfloat16()
+    drop = (0x1234567, int(round(0.1 * 65536)), 1.0 / 0.9)
+    ctx, lse = _run("uc2_attention_fwd_dropout", qkv, mask, B, S, drop)
+    d_tc = _run_bwd("uc2_attention_bwd_tc", qkv, mask, ctx, dctx, lse, B, S, drop)
+    d0 = _run_bwd("uc2_attention_bwd_dropout", qkv, mask, ctx, dctx, lse, B, S, drop)
+    scale = d0.float().abs().max().item()
+    assert torch.isfinite(d_tc.float()).all()
+    assert (d_tc.float() - d0.float()).abs().max().item() <= 1.5e-2 * scale
+
+
+def test_tc_training_step_end_to_end():
+    """A small ITM rank model (2 layers) forward + backward with both tc kernels switched in reproduces the default
+    path's loss and parameter gradients (same dropout-free computation, different attention kernels)."""
+    import cases
+    from test_model_gpu import build, dev
+    from uc2_b200._lib import lib
+    cfg = cases.config(layers=2)
+    batch = dev(cases.batch_rank())
+
+    def run(on):
+        m, _ = build("itm", cfg)
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        prev = lib().uc2_attention_tc_enable(on)
+        try:
+            loss = m(batch, compute_loss=True).mean()
+            loss.backward()
+            torch.cuda.synchronize()
+        finally:
+            lib().uc2_attention_tc_enable(prev)
+        return loss.item(), {n: p.grad.detach().float().clone() for n, p in m.named_parameters() if p.grad is not None}
+
+    l0, g0 = run(0)
+    l1, g1 = run(1)
+    assert abs(l1 - l0) <= 1e-3 * max(abs(l0), 1e-6)
+    biggest = max(g.norm().item() for g in g0.values())
+    for n, g in g0.items():
+        err = (g1[n] - g).norm().item()
+        assert err <= 2e-2 * max(g.norm().item(), 1e-3 * biggest), (n, err, g.norm().item())

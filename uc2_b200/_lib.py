@@ -89,6 +89,7 @@ _SIGS = {
     "uc2_attention_fwd_dropout": [P, P, P, P, I, I, C.c_uint, C.c_uint, F, P],
     "uc2_attention_bwd_dropout": [P, P, P, P, P, P, P, I, I, C.c_uint, C.c_uint, F, P],
     "uc2_attention_fwd_tc": [P, P, P, P, I, I, C.c_uint, C.c_uint, F, P],
+    "uc2_attention_bwd_tc": [P, P, P, P, P, P, I, I, C.c_uint, C.c_uint, F, P],
     "uc2_encoder_fwd_dropout": [P, P, P, I, I, I, C.POINTER(LayerWeights), C.POINTER(LayerActs), I, C.POINTER(Dropout),
                                 P, SZ, P],
     "uc2_encoder_bwd_dropout": [P, P, I, I, I, C.POINTER(LayerWeights), C.POINTER(LayerActs), C.POINTER(LayerGrads),

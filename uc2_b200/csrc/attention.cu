@@ -893,6 +893,8 @@ extern "C" UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long lon
                 "attention_bwd: tensors must be 16-byte aligned");
     int S_pad;
     if (int rc = attn_check(B, S, &S_pad)) return rc;
+    if (attn_tc_enabled() && S <= 160 && (reinterpret_cast<uintptr_t>(dqkv) & 31) == 0)     // opt-in, see attention_tc.cu
+        return uc2_attention_bwd_tc(qkv, attn_mask, ctx, dctx, lse, dqkv, B, S, drop_key, drop_thresh, drop_scale, stream);
     cudaStream_t s = (cudaStream_t)stream;
     const long long rows = (long long)B * S;
     ProfScope prof(s, 1, 10.0 * B * NH * (double)S * S * HD);      // 5 S x S x 64 products (7 computed)

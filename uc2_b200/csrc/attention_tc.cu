@@ -319,6 +319,328 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const TcPa
     }
 }
 
+// =================================================================================================
+// Backward, same structure, KEY-major: the recomputed scores live in TMEM as S^T (lane = key, column = query), so
+// the element-wise stage needs no row reductions (lse and delta = rowsum(dO * O) are per-COLUMN vectors in shared
+// memory, the key's mask bias is a per-thread scalar) and both halves of the query columns of a key row can go to
+// two different warps.  Per (batch, head) item and key tile u (128 keys; u = 1 holds keys 128..159):
+//     S^T_u = K_u Q^T, dP^T_u = V_u dO^T                                   (M 128, N SP, K 64; TMEM [0,160) [160,320))
+//     element-wise: P = exp2(s - lse), dropout, dS = P (dP - delta) / 8   -> Pd^T_u, dS^T_u as bf16 K-major tiles
+//     dV_u = Pd^T_u dO, dK_u = dS^T_u Q                                    (M 128, N 64, K SP; alias TMEM [0,64) [64,128))
+//     dQ_m += dS_u K_u  for the query tiles m                             (A = the dS^T tile read MN-major; TMEM [320,448))
+// Tiles of Q, K, V, dO come by TMA once per item (single buffered: the next item's loads fly under this item's
+// last epilogues); 8 element-wise warps = 4 TMEM lane quarters x 2 column halves.
+// =================================================================================================
+struct TcBwdParams {
+    const long long* mask;
+    const bf16* ctx;
+    const bf16* dctx;
+    const float* lse;
+    bf16* dqkv;
+    int B, S, SP, items;
+    DropCfg drop;
+};
+
+struct TcBwdSmem {
+    uint32_t tile_bytes, pt_bytes, off_ds, off_pd, off_vec, off_bar, total;
+    int nu, nchunk;
+};
+__host__ __device__ inline TcBwdSmem tc_bwd_smem(int S, int SP) {
+    TcBwdSmem L;
+    L.nu = S > 128 ? 2 : 1;
+    L.nchunk = (SP + 63) >> 6;
+    L.tile_bytes = SP * 128u;
+    L.pt_bytes = L.nchunk * P_CHUNK_BYTES;
+    L.off_ds = 4u * L.tile_bytes;            // [Q][K][V][dO] then dS^T, then Pd^T (so MN-major over-reads of dS^T
+    L.off_pd = L.off_ds + L.pt_bytes;        // for the padding query blocks of dQ stay inside the allocation)
+    L.off_vec = L.off_pd + L.pt_bytes;       // 2 buffers x (lse2[SP], delta[SP])
+    L.off_bar = L.off_vec + 4u * SP * 4u;
+    L.total = 1024u + L.off_bar + 128u;
+    return L;
+}
+
+constexpr uint32_t TMB_S = 0, TMB_DP = 160, TMB_DV = 0, TMB_DK = 64, TMB_DQ = 320;
+
+// 64 accumulator columns of this thread's row, scaled, -> 64 bf16 at dst
+__device__ __forceinline__ void store_row64(uint32_t taddr, bf16* dst, bool ok) {
+    uint32_t r[32];
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+        ptx::tmem_ld_32x32(taddr + c, r);
+        ptx::tmem_wait_ld();
+        if (ok) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+                ptx::stg256(dst + c + 16 * g,
+                            pack_bf16(__uint_as_float(r[16 * g + 0]), __uint_as_float(r[16 * g + 1])),
+                            pack_bf16(__uint_as_float(r[16 * g + 2]), __uint_as_float(r[16 * g + 3])),
+                            pack_bf16(__uint_as_float(r[16 * g + 4]), __uint_as_float(r[16 * g + 5])),
+                            pack_bf16(__uint_as_float(r[16 * g + 6]), __uint_as_float(r[16 * g + 7])),
+                            pack_bf16(__uint_as_float(r[16 * g + 8]), __uint_as_float(r[16 * g + 9])),
+                            pack_bf16(__uint_as_float(r[16 * g + 10]), __uint_as_float(r[16 * g + 11])),
+                            pack_bf16(__uint_as_float(r[16 * g + 12]), __uint_as_float(r[16 * g + 13])),
+                            pack_bf16(__uint_as_float(r[16 * g + 14]), __uint_as_float(r[16 * g + 15])));
+        }
+    }
+}
+__device__ __forceinline__ void store_row32(uint32_t taddr, bf16* dst, bool ok) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(taddr, r);
+    ptx::tmem_wait_ld();
+    if (ok) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+            ptx::stg256(dst + 16 * g,
+                        pack_bf16(__uint_as_float(r[16 * g + 0]), __uint_as_float(r[16 * g + 1])),
+                        pack_bf16(__uint_as_float(r[16 * g + 2]), __uint_as_float(r[16 * g + 3])),
+                        pack_bf16(__uint_as_float(r[16 * g + 4]), __uint_as_float(r[16 * g + 5])),
+                        pack_bf16(__uint_as_float(r[16 * g + 6]), __uint_as_float(r[16 * g + 7])),
+                        pack_bf16(__uint_as_float(r[16 * g + 8]), __uint_as_float(r[16 * g + 9])),
+                        pack_bf16(__uint_as_float(r[16 * g + 10]), __uint_as_float(r[16 * g + 11])),
+                        pack_bf16(__uint_as_float(r[16 * g + 12]), __uint_as_float(r[16 * g + 13])),
+                        pack_bf16(__uint_as_float(r[16 * g + 14]), __uint_as_float(r[16 * g + 15])));
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                        const TcBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
+    const int S = p.S, SP = p.SP;
+    const TcBwdSmem L = tc_bwd_smem(S, SP);
+    float* vec = reinterpret_cast<float*>(gen + L.off_vec);          // [buf][lse2 SP | delta SP]
+    const uint32_t bar = base + L.off_bar;
+    // barriers (8 B each): ld_full ld_empty sd_full[2] pds_full[2] kv_full[2] s_empty[2] dq_full dq_empty, TMEM ptr
+    const uint32_t ld_full = bar, ld_empty = bar + 8u, dq_full = bar + 80u, dq_empty = bar + 88u;
+    auto sd_full = [&](int u) { return bar + 16u + 8u * u; };
+    auto pds_full = [&](int u) { return bar + 32u + 8u * u; };
+    auto kv_full = [&](int u) { return bar + 48u + 8u * u; };
+    auto s_empty = [&](int u) { return bar + 64u + 8u * u; };
+    const uint32_t tmem_ptr_addr = bar + 96u;
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + L.off_bar + 96);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nu = L.nu;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmap_qkv);
+        ptx::prefetch_tmap(&tmap_do);
+        ptx::mbar_init(ld_full, 1);
+        ptx::mbar_init(ld_empty, 1);
+        for (int u = 0; u < 2; ++u) {
+            const int na = 2 * active_warps(S, u);            // two column halves per active lane quarter
+            ptx::mbar_init(sd_full(u), 1);
+            ptx::mbar_init(pds_full(u), na > 0 ? na : 1);
+            ptx::mbar_init(kv_full(u), 1);
+            ptx::mbar_init(s_empty(u), na > 0 ? na : 1);
+        }
+        ptx::mbar_init(dq_full, 1);
+        ptx::mbar_init(dq_empty, 2 * active_warps(S, 0));
+        ptx::fence_barrier_init();
+        ptx::fence_proxy_async();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_ptr_addr, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    griddep_sync();
+
+    const uint32_t sQ = base, sK = sQ + L.tile_bytes, sV = sK + L.tile_bytes, sdO = sV + L.tile_bytes;
+    const uint32_t sDS = base + L.off_ds, sPD = base + L.off_pd;
+
+    if (warp == 0) {
+        // ===================================== producer =====================================
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+                const int b = item / NH, h = item - b * NH;
+                ptx::mbar_wait(ld_empty, (it & 1u) ^ 1u);          // every MMA of the previous item retired
+                ptx::mbar_arrive_expect_tx(ld_full, 4u * L.tile_bytes);
+                ptx::tma_load_2d(sQ, &tmap_qkv, ld_full, h * HD, b * S);
+                ptx::tma_load_2d(sK, &tmap_qkv, ld_full, HID + h * HD, b * S);
+                ptx::tma_load_2d(sV, &tmap_qkv, ld_full, 2 * HID + h * HD, b * S);
+                ptx::tma_load_2d(sdO, &tmap_do, ld_full, h * HD, b * S);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer ===================================
+        if (lane == 0) {
+            const uint32_t idesc_s = ptx::idesc_bf16_f32(128, SP, false, false);
+            const uint32_t idesc_kv = ptx::idesc_bf16_f32(128, HD, false, true);
+            const uint32_t idesc_dq = ptx::idesc_bf16_f32(128, HD, true, true);
+            int it = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+                const uint32_t itp = it & 1u;
+                ptx::mbar_wait(ld_full, itp);
+                ptx::tc_fence_after();
+                for (int u = 0; u < nu; ++u) {
+                    // TMEM [0,320) is free once the dV / dK of the previous key tile have been read out
+                    if (u == 0) ptx::mbar_wait(s_empty(nu - 1), itp ^ 1u);
+                    else ptx::mbar_wait(s_empty(u - 1), itp);
+                    ptx::tc_fence_after();
+                    // key tile 1 reads 128 rows from row 128 of K / V on; rows past SP are the following tiles
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k)
+                        ptx::umma_bf16(tmem_base + TMB_S, ptx::smem_desc_sw128(sK + u * 16384u + k * 32u, 16u, 1024u),
+                                       ptx::smem_desc_sw128(sQ + k * 32u, 16u, 1024u), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k)
+                        ptx::umma_bf16(tmem_base + TMB_DP, ptx::smem_desc_sw128(sV + u * 16384u + k * 32u, 16u, 1024u),
+                                       ptx::smem_desc_sw128(sdO + k * 32u, 16u, 1024u), idesc_s, k > 0 ? 1u : 0u);
+                    ptx::umma_commit(sd_full(u));
+
+                    ptx::mbar_wait(pds_full(u), itp);              // Pd^T_u, dS^T_u written; S^T, dP^T read
+                    if (u == 0) ptx::mbar_wait(dq_empty, itp ^ 1u);   // previous item's dQ read out
+                    ptx::tc_fence_after();
+                    for (int kk = 0; kk < SP / 16; ++kk) {         // K dimension = queries
+                        const uint32_t a_off = (kk >> 2) * P_CHUNK_BYTES + (kk & 3) * 32u;
+                        ptx::umma_bf16(tmem_base + TMB_DV, ptx::smem_desc_sw128(sPD + a_off, 16u, 1024u),
+                                       ptx::smem_desc_sw128(sdO + kk * 2048u, 8192u, 1024u), idesc_kv, kk > 0 ? 1u : 0u);
+                    }
+                    for (int kk = 0; kk < SP / 16; ++kk) {
+                        const uint32_t a_off = (kk >> 2) * P_CHUNK_BYTES + (kk & 3) * 32u;
+                        ptx::umma_bf16(tmem_base + TMB_DK, ptx::smem_desc_sw128(sDS + a_off, 16u, 1024u),
+                                       ptx::smem_desc_sw128(sQ + kk * 2048u, 8192u, 1024u), idesc_kv, kk > 0 ? 1u : 0u);
+                    }
+                    // dQ_m += dS[queries of tile m, keys of tile u] K_u: A is the dS^T tile read MN-major (64-query
+                    // blocks P_CHUNK_BYTES apart, 16 key rows per K step), B = K rows of tile u, MN-major
+                    const int ksteps = (u == 0 ? (SP < 128 ? SP : 128) : SP - 128) / 16;
+                    for (int m = 0; m < nu; ++m)
+                        for (int kk = 0; kk < ksteps; ++kk)
+                            ptx::umma_bf16(tmem_base + TMB_DQ + m * 64u,
+                                           ptx::smem_desc_sw128(sDS + m * 2u * P_CHUNK_BYTES + kk * 2048u, P_CHUNK_BYTES, 1024u),
+                                           ptx::smem_desc_sw128(sK + u * 16384u + kk * 2048u, 8192u, 1024u), idesc_dq,
+                                           (u > 0 || kk > 0) ? 1u : 0u);
+                    ptx::umma_commit(kv_full(u));
+                }
+                ptx::umma_commit(ld_empty);
+                ptx::umma_commit(dq_full);
+            }
+        }
+    } else {
+        // ===================================== element-wise warps ============================
+        const int q = warp & 3;                         // TMEM lane quarter
+        const int half = (warp - 2) >> 2;               // which half of the query columns / of the outputs
+        const int ew = warp - 2;
+        const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+        const int kr = q * 32 + lane;                   // row inside a 128-row tile
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        const int csplit = ((SP / 16 + 1) / 2) * 16;
+        const int c_begin = half == 0 ? 0 : csplit, c_end = half == 0 ? csplit : SP;
+        int it = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+            const uint32_t itp = it & 1u;
+            const int b = item / NH, h = item - b * NH;
+            const long long row0 = (long long)b * S;
+            // ---- per-query vectors: lse in the exp2 domain (+inf for padding columns -> P = 0), delta
+            float* lse2 = vec + (it & 1) * 2 * SP;
+            float* delta = lse2 + SP;
+            {
+                const float* Lg = p.lse + ((long long)b * NH + h) * S;
+                for (int i = threadIdx.x - 64; i < SP; i += 256) lse2[i] = i < S ? Lg[i] * LOG2E : INFINITY;
+                for (int r0 = ew * 4; r0 < SP; r0 += 32) {
+                    const int r = r0 + (lane >> 3), c8 = (lane & 7) * 8;
+                    float acc = 0.f;
+                    if (r < S) {
+                        float a[8], d[8];
+                        load8_bf16(p.ctx + (row0 + r) * HID + h * HD + c8, a);
+                        load8_bf16(p.dctx + (row0 + r) * HID + h * HD + c8, d);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc = fmaf(a[k], d[k], acc);
+                    }
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                    if ((lane & 7) == 0 && r < SP) delta[r] = acc;
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");         // the eight element-wise warps only
+            const uint32_t hkey = drop_head_key(p.drop.key, b * NH + h);
+
+            for (int u = 0; u < nu; ++u) {
+                if (u * 128 + q * 32 >= S) continue;               // no key rows of this tile in this lane quarter
+                const int key = u * 128 + kr;
+                const bool key_ok = key < S;
+                const float bias = key_ok ? (p.mask[row0 + key] != 0 ? 0.f : MASK_LOG2) : -INFINITY;
+                ptx::mbar_wait(sd_full(u), itp);
+                ptx::tc_fence_after();
+                const uint32_t prow = static_cast<uint32_t>(kr) * 128u;
+                for (int c = c_begin; c < c_end; c += 16) {
+                    uint32_t rs[16], rd[16], pd[8], ds[8];
+                    ptx::tmem_ld_32x16(tmem_base + lane_sel + TMB_S + c, rs);
+                    ptx::tmem_ld_32x16(tmem_base + lane_sel + TMB_DP + c, rd);
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        const float2 l2 = *reinterpret_cast<const float2*>(lse2 + c + j);
+                        const float2 de = *reinterpret_cast<const float2*>(delta + c + j);
+                        const float p0 = fast_ex2(fmaf(__uint_as_float(rs[j]), SCALE_LOG2, bias) - l2.x);
+                        const float p1 = fast_ex2(fmaf(__uint_as_float(rs[j + 1]), SCALE_LOG2, bias) - l2.y);
+                        float pd0 = p0, pd1 = p1, dp0 = __uint_as_float(rd[j]), dp1 = __uint_as_float(rd[j + 1]);
+                        if (p.drop.thresh) {
+                            // element (query c + j, key): the same counter stream as the forward (idx = query * S + key)
+                            const uint32_t i0 = static_cast<uint32_t>(c + j) * static_cast<uint32_t>(S) + key;
+                            const bool k0 = drop_keep(hkey, i0, p.drop.thresh);
+                            const bool k1 = drop_keep(hkey, i0 + static_cast<uint32_t>(S), p.drop.thresh);
+                            pd0 = k0 ? p0 * p.drop.scale : 0.f; dp0 = k0 ? dp0 * p.drop.scale : 0.f;
+                            pd1 = k1 ? p1 * p.drop.scale : 0.f; dp1 = k1 ? dp1 * p.drop.scale : 0.f;
+                        }
+                        pd[j / 2] = pack_bf16(pd0, pd1);
+                        ds[j / 2] = pack_bf16(p0 * (dp0 - de.x) * 0.125f, p1 * (dp1 - de.y) * 0.125f);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const uint32_t q0 = c + 8 * g;             // 8 queries = one 16-byte unit of the swizzled row
+                        const uint32_t off = (q0 >> 6) * P_CHUNK_BYTES + prow + ((((q0 & 63u) >> 3) ^ sw) << 4);
+                        ptx::st_shared_v4(sPD + off, pd[4 * g], pd[4 * g + 1], pd[4 * g + 2], pd[4 * g + 3]);
+                        ptx::st_shared_v4(sDS + off, ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]);
+                    }
+                }
+                ptx::fence_proxy_async();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(pds_full(u));
+
+                // dV_u (half 0) / dK_u (half 1) of this key row -> dqkv
+                ptx::mbar_wait(kv_full(u), itp);
+                ptx::tc_fence_after();
+                bf16* dst = p.dqkv + (row0 + key) * QKV_LD + (half == 0 ? 2 * HID : HID) + h * HD;
+                store_row64(tmem_base + lane_sel + (half == 0 ? TMB_DV : TMB_DK), dst, key_ok);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(s_empty(u));
+            }
+
+            // dQ: query rows in the lanes; half = which 32 of the 64 columns
+            if (q * 32 < S) {
+                ptx::mbar_wait(dq_full, itp);
+                ptx::tc_fence_after();
+                store_row32(tmem_base + lane_sel + TMB_DQ + half * 32, p.dqkv + (row0 + kr) * QKV_LD + h * HD + half * 32,
+                            kr < S);
+                if (nu == 2 && q == 0)
+                    store_row32(tmem_base + TMB_DQ + 64u + half * 32,
+                                p.dqkv + (row0 + 128 + lane) * QKV_LD + h * HD + half * 32, 128 + lane < S);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(dq_empty);
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -406,4 +728,61 @@ extern "C" UC2_API int uc2_attention_fwd_tc(const void* qkv, const long long* at
                                      (cudaStream_t)stream, 1, tmap, p);
     UC2_REQUIRE(e == cudaSuccess, UC2_ERR_CUDA, "attention_fwd_tc launch failed: %s", cudaGetErrorString(e));
     return check_last("attention_fwd_tc_kernel");
+}
+
+namespace {
+int make_head_tmap(CUtensorMap* m, const void* base, long long rows, int cols, int box_rows, const char* what) {
+    EncodeTiledFn enc = encode_fn();
+    UC2_REQUIRE(enc != nullptr, UC2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols) * 2};
+    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UC2_REQUIRE(r == CUDA_SUCCESS, UC2_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d box_rows=%d",
+                what, (int)r, rows, cols, box_rows);
+    return UC2_OK;
+}
+}  // namespace
+
+extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* attn_mask, const void* ctx,
+                                            const void* dctx, const float* lse, void* dqkv, int B, int S,
+                                            unsigned int drop_key, unsigned int drop_thresh, float drop_scale,
+                                            void* stream) {
+    if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(qkv && attn_mask && ctx && dctx && lse && dqkv, UC2_ERR_ARG, "attention_bwd_tc: null pointer");
+    UC2_REQUIRE(B > 0 && S > 0, UC2_ERR_ARG, "attention_bwd_tc: bad shape B=%d S=%d", B, S);
+    UC2_REQUIRE(drop_thresh < 65536u, UC2_ERR_ARG, "attention_bwd_tc: drop_thresh must be < 65536");
+    const int SP = (S + 15) / 16 * 16;
+    UC2_REQUIRE(SP <= TC_MAX_SP, UC2_ERR_UNSUPPORTED, "attention_bwd_tc: S=%d > %d", S, TC_MAX_SP);
+    UC2_REQUIRE(aligned16(qkv) && aligned16(ctx) && aligned16(dctx) && (reinterpret_cast<uintptr_t>(dqkv) & 31) == 0,
+                UC2_ERR_ARG, "attention_bwd_tc: qkv / ctx / dctx must be 16-byte and dqkv 32-byte aligned");
+    CUtensorMap tq, tdo;
+    if (int rc = make_head_tmap(&tq, qkv, (long long)B * S, QKV_LD, SP, "attention_bwd_tc(qkv)")) return rc;
+    if (int rc = make_head_tmap(&tdo, dctx, (long long)B * S, HID, SP, "attention_bwd_tc(dctx)")) return rc;
+    const TcBwdSmem L = tc_bwd_smem(S, SP);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(tc_bwd_smem(TC_MAX_SP, TC_MAX_SP).total));
+    });
+    UC2_REQUIRE(attr_err == cudaSuccess, UC2_ERR_CUDA, "attention_bwd_tc: cudaFuncSetAttribute failed: %s",
+                cudaGetErrorString(attr_err));
+    TcBwdParams p;
+    p.mask = attn_mask;
+    p.ctx = static_cast<const bf16*>(ctx);
+    p.dctx = static_cast<const bf16*>(dctx);
+    p.lse = lse;
+    p.dqkv = static_cast<bf16*>(dqkv);
+    p.B = B; p.S = S; p.SP = SP; p.items = B * NH;
+    p.drop = DropCfg{drop_key, drop_thresh, drop_scale};
+    const int grid = p.items < num_sms() ? p.items : num_sms();
+    ProfScope prof((cudaStream_t)stream, 1, 10.0 * B * NH * (double)S * S * HD);
+    const cudaError_t e = launch_pdl(attention_bwd_tc_kernel, dim3(grid), dim3(TC_THREADS), L.total,
+                                     (cudaStream_t)stream, 1, tq, tdo, p);
+    UC2_REQUIRE(e == cudaSuccess, UC2_ERR_CUDA, "attention_bwd_tc launch failed: %s", cudaGetErrorString(e));
+    return check_last("attention_bwd_tc_kernel");
 }
