@@ -641,23 +641,6 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(f);
-    });
-    return fn;
-}
-
 std::atomic<int> g_tc_enabled{-1};      // -1: not decided yet (environment), 0 / 1
 
 }  // namespace
@@ -693,20 +676,10 @@ extern "C" UC2_API int uc2_attention_fwd_tc(const void* qkv, const long long* at
     UC2_REQUIRE(SP <= TC_MAX_SP, UC2_ERR_UNSUPPORTED, "attention_fwd_tc: S=%d > %d", S, TC_MAX_SP);
     UC2_REQUIRE(aligned16(qkv) && (reinterpret_cast<uintptr_t>(ctx) & 31) == 0, UC2_ERR_ARG,
                 "attention_fwd_tc: qkv must be 16-byte and ctx 32-byte aligned");
-    EncodeTiledFn enc = encode_fn();
-    UC2_REQUIRE(enc != nullptr, UC2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     // qkv as a 2-D bf16 tensor [B*S][2304]; one box = the SP x 64 tile of one head's Q, K or V (rows past B*S are
     // zero-filled, rows past S inside the box belong to the next sample and are masked / never stored)
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(QKV_LD), static_cast<cuuint64_t>(B) * S};
-    const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(QKV_LD) * 2};
-    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(SP)};
-    const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    UC2_REQUIRE(r == CUDA_SUCCESS, UC2_ERR_CUDA, "attention_fwd_tc: cuTensorMapEncodeTiled failed (%d) B=%d S=%d", (int)r,
-                B, S);
+    if (int rc = make_tmap(&tmap, qkv, (long long)B * S, QKV_LD, QKV_LD, SP)) return rc;
     const TcSmem L = tc_smem(S, SP);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -730,23 +703,6 @@ extern "C" UC2_API int uc2_attention_fwd_tc(const void* qkv, const long long* at
     return check_last("attention_fwd_tc_kernel");
 }
 
-namespace {
-int make_head_tmap(CUtensorMap* m, const void* base, long long rows, int cols, int box_rows, const char* what) {
-    EncodeTiledFn enc = encode_fn();
-    UC2_REQUIRE(enc != nullptr, UC2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols) * 2};
-    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
-    const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    UC2_REQUIRE(r == CUDA_SUCCESS, UC2_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d box_rows=%d",
-                what, (int)r, rows, cols, box_rows);
-    return UC2_OK;
-}
-}  // namespace
-
 extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* attn_mask, const void* ctx,
                                             const void* dctx, const float* lse, void* dqkv, int B, int S,
                                             unsigned int drop_key, unsigned int drop_thresh, float drop_scale,
@@ -760,8 +716,8 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     UC2_REQUIRE(aligned16(qkv) && aligned16(ctx) && aligned16(dctx) && (reinterpret_cast<uintptr_t>(dqkv) & 31) == 0,
                 UC2_ERR_ARG, "attention_bwd_tc: qkv / ctx / dctx must be 16-byte and dqkv 32-byte aligned");
     CUtensorMap tq, tdo;
-    if (int rc = make_head_tmap(&tq, qkv, (long long)B * S, QKV_LD, SP, "attention_bwd_tc(qkv)")) return rc;
-    if (int rc = make_head_tmap(&tdo, dctx, (long long)B * S, HID, SP, "attention_bwd_tc(dctx)")) return rc;
+    if (int rc = make_tmap(&tq, qkv, (long long)B * S, QKV_LD, QKV_LD, SP)) return rc;
+    if (int rc = make_tmap(&tdo, dctx, (long long)B * S, HID, HID, SP)) return rc;
     const TcBwdSmem L = tc_bwd_smem(S, SP);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;

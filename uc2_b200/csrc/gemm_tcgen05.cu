@@ -541,43 +541,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(f);
-    });
-    return fn;
-}
-
-// 2-D bf16 tensor [rows][cols] with row pitch ld elements; box = [box_rows][64 cols], SWIZZLE_128B.
-int make_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
-    EncodeTiledFn enc = get_encode_fn();
-    UC2_REQUIRE(enc != nullptr, UC2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
-    cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    UC2_REQUIRE(r == CUDA_SUCCESS, UC2_ERR_CUDA,
-                "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box_rows=%d base=%p", (int)r, rows,
-                cols, ld, box_rows, base);
-    return UC2_OK;
-}
+// tensormap_encoder() / make_tmap() (2-D bf16, [box_rows][64] SWIZZLE_128B boxes): runtime.cu, declared in common.cuh
 
 // fp32 output [rows][cols], row pitch ld elements; box = 32 rows x 32 columns (128 B), SWIZZLE_128B
 int make_tmap_out_f32(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld) {
-    EncodeTiledFn enc = get_encode_fn();
+    EncodeTiledFn enc = tensormap_encoder();
     UC2_REQUIRE(enc != nullptr, UC2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};

@@ -53,6 +53,39 @@ int num_sms() {
     return sms;
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA descriptors
+// ---------------------------------------------------------------------------------------------
+EncodeTiledFn tensormap_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    });
+    return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] with row pitch ld elements; box = [box_rows][64 cols], SWIZZLE_128B.
+int make_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn enc = tensormap_encoder();
+    UC2_REQUIRE(enc != nullptr, UC2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UC2_REQUIRE(r == CUDA_SUCCESS, UC2_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box_rows=%d base=%p", (int)r, rows,
+                cols, ld, box_rows, base);
+    return UC2_OK;
+}
+
 bool pdl_enabled() {
     static int on = -1;
     if (on < 0) {
