@@ -26,3 +26,10 @@ fi
 # timing, default kernels vs the tc kernels
 run bench_mma_sync python scripts/attn_bench.py
 UC2_ATTN_TCGEN05=1 run bench_tcgen05 python scripts/attn_bench.py
+# the whole ITM step both ways (the second only means something if every stage above exited 0)
+run bench_itm_default python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+UC2_ATTN_TCGEN05=1 run bench_itm_tcgen05 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+# one full ncu capture of each tc kernel (never a timing source)
+UC2_ATTN_TCGEN05=1 timeout 600 ncu --set full --clock-control none --import-source on \
+    -k regex:attention_.*_tc_kernel -c 2 -f -o "$out/attn_tc" python scripts/attn_bench.py > "$out/ncu.log" 2>&1
+echo "ncu exit $?" | tee -a "$out/summary.txt"
