@@ -2,7 +2,7 @@
 """Attention fwd/bwd timing + check against a torch fp32 reference (key-padding mask, fixed list of shapes).
 With UC2_ATTN_TCGEN05=1 in the environment the public entry points route S <= 160 to the experimental tcgen05
 kernels (csrc/attention_tc.cu), so the same script times those."""
-import os, sys, math, torch
+import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from uc2_b200._lib import call, stream
 

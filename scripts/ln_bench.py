@@ -2,7 +2,6 @@
 """LayerNorm fwd/bwd and column-sum bandwidth at the bench token count (HBM roofline check)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from uc2_b200 import _lib
 from uc2_b200._lib import call, stream
 
 def t(fn, reps=20):

@@ -2,7 +2,7 @@
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np, torch
+import torch  # noqa: F401  (initialises CUDA before the extension loads)
 import cases
 from oracle import uc2_oracle as O
 from uc2_b200 import itm, model
