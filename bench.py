@@ -552,7 +552,8 @@ def main():
             "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
             "launches_per_step": int(n_k[0]), "gemm_ms_per_step": ms_k[0], "gemm_share_of_step": ms_k[0] / ms_step,
             "attention_ms_per_step": ms_k[1],
-            "attention_tflops": work_k[1] / (ms_k[1] * 1e-3) / 1e12 if ms_k[1] > 0 else 0.0}
+            "attention_tflops": work_k[1] / (ms_k[1] * 1e-3) / 1e12 if ms_k[1] > 0 else 0.0,
+            "attention_kernels": "tcgen05 (experimental, S <= 160)" if _lib.attention_tc_enabled() else "mma.sync"}
     roof["traffic"], roof["traffic_source"] = ncu_traffic()
 
     if world > 1:

@@ -170,6 +170,13 @@ def call(name, *args):
     check(getattr(lib(), name)(*args), name)
 
 
+def attention_tc_enabled():
+    """Whether the public attention entry points currently route S <= 160 to the experimental tcgen05 kernels."""
+    prev = lib().uc2_attention_tc_enable(0)
+    lib().uc2_attention_tc_enable(prev)
+    return bool(prev)
+
+
 def launch_count():
     return int(lib().uc2_launch_count())
 
