@@ -146,3 +146,17 @@ def test_backward_operands(S):
                 assert np.array_equal(a[:qrows], dST[16 * kk:16 * kk + 16, 128 * m:128 * m + qrows].T)
                 b = sm.read_mn_major(sK + u * 16384 + kk * 2048, 8192, 1024, 64)
                 assert np.array_equal(b, K[128 * u + 16 * kk:128 * u + 16 * kk + 16].T)
+
+
+def test_switch_is_off_by_default_and_toggles(monkeypatch):
+    """The experimental kernels must never be the default path: the switch starts off (no UC2_ATTN_TCGEN05 in the
+    environment of this test run) and uc2_attention_tc_enable returns the previous setting."""
+    import os
+    from uc2_b200 import _lib
+    if os.environ.get("UC2_ATTN_TCGEN05") == "1":
+        pytest.skip("switch forced on through the environment")
+    assert _lib.attention_tc_enabled() is False
+    assert _lib.lib().uc2_attention_tc_enable(1) == 0
+    assert _lib.attention_tc_enabled() is True
+    assert _lib.lib().uc2_attention_tc_enable(0) == 1
+    assert _lib.attention_tc_enabled() is False
