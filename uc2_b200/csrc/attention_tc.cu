@@ -13,7 +13,7 @@
 //                 max / row sum need no shuffles; two passes over the row in TMEM (max, then exp2 + sum + the
 //                 counter-hash dropout of attention.cu), P written as bf16 into the K-major SWIZZLE_128B
 //                 shared-memory layout the MMA's A descriptor reads; then the epilogue O / rowsum -> ctx, lse.
-//   TMEM: S_0 [0,160) S_1 [160,320) O_0 [320,384) O_1 [384,448) of 512 columns.
+//   TMEM: S_0 [0,160) S_1 [192,352) O_0 [384,448) O_1 [448,512) of 512 columns.
 //
 // STATUS: written and compiled (ptxas / SASS checked) at the end of round 1 after the round's GPU budget was
 // spent -- NOT YET RUN ON HARDWARE.  It is therefore off by default: uc2_attention_fwd(_dropout) only route here
@@ -38,7 +38,8 @@ constexpr int TC_THREADS = 320;              // TMA warp, MMA warp, 2 x 4 softma
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float SCALE_LOG2 = 0.125f * LOG2E;
 constexpr float MASK_LOG2 = -10000.0f * LOG2E;
-constexpr uint32_t TM_S = 0, TM_S_STRIDE = 160, TM_O = 320, TM_O_STRIDE = 64, TMEM_COLS = 512;
+// accumulator column bases kept on multiples of 64 (the 160-column S tiles get 192-column slots)
+constexpr uint32_t TM_S = 0, TM_S_STRIDE = 192, TM_O = 384, TM_O_STRIDE = 64, TMEM_COLS = 512;
 constexpr uint32_t P_CHUNK_BYTES = 128 * 128;   // 128 query rows x 64 keys of bf16
 
 struct TcParams {
@@ -324,10 +325,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const TcPa
 // the element-wise stage needs no row reductions (lse and delta = rowsum(dO * O) are per-COLUMN vectors in shared
 // memory, the key's mask bias is a per-thread scalar) and both halves of the query columns of a key row can go to
 // two different warps.  Per (batch, head) item and key tile u (128 keys; u = 1 holds keys 128..159):
-//     S^T_u = K_u Q^T, dP^T_u = V_u dO^T                                   (M 128, N SP, K 64; TMEM [0,160) [160,320))
+//     S^T_u = K_u Q^T, dP^T_u = V_u dO^T                                   (M 128, N SP, K 64; TMEM [0,160) [192,352))
 //     element-wise: P = exp2(s - lse), dropout, dS = P (dP - delta) / 8   -> Pd^T_u, dS^T_u as bf16 K-major tiles
 //     dV_u = Pd^T_u dO, dK_u = dS^T_u Q                                    (M 128, N 64, K SP; alias TMEM [0,64) [64,128))
-//     dQ_m += dS_u K_u  for the query tiles m                             (A = the dS^T tile read MN-major; TMEM [320,448))
+//     dQ_m += dS_u K_u  for the query tiles m                             (A = the dS^T tile read MN-major; TMEM [384,512))
 // Tiles of Q, K, V, dO come by TMA once per item (single buffered: the next item's loads fly under this item's
 // last epilogues); 8 element-wise warps = 4 TMEM lane quarters x 2 column halves.
 // =================================================================================================
@@ -359,7 +360,7 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int S, int SP) {
     return L;
 }
 
-constexpr uint32_t TMB_S = 0, TMB_DP = 160, TMB_DV = 0, TMB_DK = 64, TMB_DQ = 320;
+constexpr uint32_t TMB_S = 0, TMB_DP = 192, TMB_DV = 0, TMB_DK = 64, TMB_DQ = 384;
 
 // 64 accumulator columns of this thread's row, scaled, -> 64 bf16 at dst
 __device__ __forceinline__ void store_row64(uint32_t taddr, bf16* dst, bool ok) {
@@ -480,7 +481,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 ptx::mbar_wait(ld_full, itp);
                 ptx::tc_fence_after();
                 for (int u = 0; u < nu; ++u) {
-                    // TMEM [0,320) is free once the dV / dK of the previous key tile have been read out
+                    // TMEM [0,352) is free once the dV / dK of the previous key tile have been read out
                     if (u == 0) ptx::mbar_wait(s_empty(nu - 1), itp ^ 1u);
                     else ptx::mbar_wait(s_empty(u - 1), itp);
                     ptx::tc_fence_after();
