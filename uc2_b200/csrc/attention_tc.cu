@@ -642,6 +642,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     }
 }
 
+// Both kernels allocate all 512 TMEM columns, so two of their CTAs must never share an SM (the second would sit in
+// tcgen05.alloc until the first one's whole persistent loop is over): short sequences, whose tiles are small, still
+// ask for more than half of the SM's shared memory.
+inline size_t exclusive_smem(uint32_t need) { return need > 120u * 1024u ? need : 120u * 1024u; }
+
 std::atomic<int> g_tc_enabled{-1};      // -1: not decided yet (environment), 0 / 1
 
 }  // namespace
@@ -698,7 +703,7 @@ extern "C" UC2_API int uc2_attention_fwd_tc(const void* qkv, const long long* at
     p.drop = DropCfg{drop_key, drop_thresh, drop_scale};
     const int grid = p.items < num_sms() ? p.items : num_sms();
     ProfScope prof((cudaStream_t)stream, 1, 4.0 * B * NH * (double)S * S * HD);
-    const cudaError_t e = launch_pdl(attention_fwd_tc_kernel, dim3(grid), dim3(TC_THREADS), L.total,
+    const cudaError_t e = launch_pdl(attention_fwd_tc_kernel, dim3(grid), dim3(TC_THREADS), exclusive_smem(L.total),
                                      (cudaStream_t)stream, 1, tmap, p);
     UC2_REQUIRE(e == cudaSuccess, UC2_ERR_CUDA, "attention_fwd_tc launch failed: %s", cudaGetErrorString(e));
     return check_last("attention_fwd_tc_kernel");
@@ -738,7 +743,7 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     p.drop = DropCfg{drop_key, drop_thresh, drop_scale};
     const int grid = p.items < num_sms() ? p.items : num_sms();
     ProfScope prof((cudaStream_t)stream, 1, 10.0 * B * NH * (double)S * S * HD);
-    const cudaError_t e = launch_pdl(attention_bwd_tc_kernel, dim3(grid), dim3(TC_THREADS), L.total,
+    const cudaError_t e = launch_pdl(attention_bwd_tc_kernel, dim3(grid), dim3(TC_THREADS), exclusive_smem(L.total),
                                      (cudaStream_t)stream, 1, tq, tdo, p);
     UC2_REQUIRE(e == cudaSuccess, UC2_ERR_CUDA, "attention_bwd_tc launch failed: %s", cudaGetErrorString(e));
     return check_last("attention_bwd_tc_kernel");
