@@ -20,6 +20,9 @@
 // after uc2_attention_tc_enable(1) or with UC2_ATTN_TCGEN05=1 in the environment, and its parity test
 // (tests/test_attention_tc_gpu.py) runs only with UC2_TEST_EXPERIMENTAL=1.  Results are defined to be those of
 // attention_fwd_bh_kernel (same masks, same dropout stream, same lse), so the existing backward pairs with it.
+// Checked on the CPU meanwhile (tests/test_attention_tc_{layout,protocol,dataflow}_cpu.py): every MMA operand as
+// read through its descriptor, the mbarrier protocol under random interleavings, and the data path on real numbers.
+// If you change an offset, a stride, a barrier count or a parity here, change the mirrored constant there.
 #include <atomic>
 #include <mutex>
 #include <stdlib.h>
