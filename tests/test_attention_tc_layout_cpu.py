@@ -66,7 +66,7 @@ def tagged(tag, rows, cols=64):
     return tag * 1e6 + r * 1e3 + c
 
 
-@pytest.mark.parametrize("S", [160, 150, 129, 128, 76, 33, 16])
+@pytest.mark.parametrize("S", [160, 159, 150, 145, 144, 129, 128, 127, 100, 97, 96, 76, 65, 64, 33, 17, 16, 15, 1])
 def test_forward_operands(S):
     SP = (S + 15) // 16 * 16
     nt = 2 if S > 128 else 1
@@ -102,7 +102,7 @@ def test_forward_operands(S):
             assert np.array_equal(b, V[16 * kk:16 * kk + 16, :].T)
 
 
-@pytest.mark.parametrize("S", [160, 150, 129, 128, 76, 33, 16])
+@pytest.mark.parametrize("S", [160, 159, 150, 145, 144, 129, 128, 127, 100, 97, 96, 76, 65, 64, 33, 17, 16, 15, 1])
 def test_backward_operands(S):
     SP = (S + 15) // 16 * 16
     nu = 2 if S > 128 else 1

@@ -262,13 +262,13 @@ def backward_protocol(S, items, rng):
     assert len(done) == items * 8
 
 
-@pytest.mark.parametrize("S", [160, 129, 128, 100, 76, 33, 16])
+@pytest.mark.parametrize("S", [160, 145, 129, 128, 100, 97, 96, 76, 65, 33, 16, 1])
 @pytest.mark.parametrize("seed", range(6))
 def test_forward_protocol(S, seed):
     forward_protocol(S, items=7, rng=random.Random(1000 * S + seed))
 
 
-@pytest.mark.parametrize("S", [160, 129, 128, 100, 76, 33, 16])
+@pytest.mark.parametrize("S", [160, 145, 129, 128, 100, 97, 96, 76, 65, 33, 16, 1])
 @pytest.mark.parametrize("seed", range(6))
 def test_backward_protocol(S, seed):
     backward_protocol(S, items=7, rng=random.Random(1000 * S + seed))
