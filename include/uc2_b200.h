@@ -204,7 +204,8 @@ UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long long* attn_mas
 UC2_API int uc2_attention_fwd_tc(const void* qkv, const long long* attn_mask, void* ctx, float* lse, int B, int S,
                                  unsigned int drop_key, unsigned int drop_thresh, float drop_scale, void* stream);
 /* ... and the backward (dqkv fully overwritten for the B*S rows; delta = rowsum(dO * O) is computed inside, so
- * there is no workspace argument).  dqkv must be 32-byte aligned. */
+ * there is no workspace argument).  dqkv must be 32-byte aligned.  UC2_ATTN_TC_BWD_SPLIT=4 in the environment runs
+ * it with 16 instead of 8 element-wise warps (a tuning knob; same results). */
 UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* attn_mask, const void* ctx, const void* dctx,
                                  const float* lse, void* dqkv, int B, int S, unsigned int drop_key,
                                  unsigned int drop_thresh, float drop_scale, void* stream);

@@ -19,6 +19,8 @@ run fwd_all     python -m pytest tests/test_attention_tc_gpu.py -x -q -k "forwar
 run bwd_small   python -m pytest tests/test_attention_tc_gpu.py -x -q -k "backward_matches and (2-16 or 5-33)"
 run bwd_all     python -m pytest tests/test_attention_tc_gpu.py -x -q -k "backward"
 run end_to_end  python -m pytest tests/test_attention_tc_gpu.py -x -q -k "end_to_end"
+# the backward with four instead of two element-wise warps per TMEM lane quarter (16 warps; tuning knob)
+UC2_ATTN_TC_BWD_SPLIT=4 run bwd_all_split4 python -m pytest tests/test_attention_tc_gpu.py -x -q -k "backward"
 # memcheck of one small forward + backward if anything above failed
 if grep -q "exit [1-9]" "$out/summary.txt"; then
     run sanitizer compute-sanitizer --tool memcheck python -m pytest tests/test_attention_tc_gpu.py -x -q -k "2-16"
@@ -26,6 +28,7 @@ fi
 # timing, default kernels vs the tc kernels
 run bench_mma_sync python scripts/attn_bench.py
 UC2_ATTN_TCGEN05=1 run bench_tcgen05 python scripts/attn_bench.py
+UC2_ATTN_TCGEN05=1 UC2_ATTN_TC_BWD_SPLIT=4 run bench_tcgen05_split4 python scripts/attn_bench.py
 # the whole ITM step both ways (the second only means something if every stage above exited 0)
 run bench_itm_default python bench.py --steps 20 --warmup 5 --no-cpu-baseline
 UC2_ATTN_TCGEN05=1 run bench_itm_tcgen05 python bench.py --steps 20 --warmup 5 --no-cpu-baseline

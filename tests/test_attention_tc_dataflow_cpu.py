@@ -124,7 +124,7 @@ def forward_walk(S, SP, Q, K, V, mask, thresh, scale, hkey):
     return ctx, lse
 
 
-def backward_walk(S, SP, Q, K, V, dO, ctx, lse, mask, thresh, scale, hkey):
+def backward_walk(S, SP, Q, K, V, dO, ctx, lse, mask, thresh, scale, hkey, nsplit=2):
     nu, nchunk = (2 if S > 128 else 1), (SP + 63) // 64
     tile, pt = SP * 128, ((SP + 63) // 64) * P_CHUNK
     off_ds, off_pd = 4 * tile, 4 * tile + pt
@@ -135,21 +135,22 @@ def backward_walk(S, SP, Q, K, V, dO, ctx, lse, mask, thresh, scale, hkey):
         sm.tma_box(base, mat)
     lse2 = np.where(np.arange(SP) < S, np.pad(lse, (0, SP - S)) * LOG2E, np.inf).astype(np.float32)
     delta = np.where(np.arange(SP) < S, np.pad((bf(ctx) * dO[:S]).sum(1), (0, SP - S)), 0.0).astype(np.float32)
-    csplit = ((SP // 16 + 1) // 2) * 16
+    nch = SP // 16
+    per = (nch + nsplit - 1) // nsplit                                # 16-column chunks per part
     dqkv = {n: np.full((S, HD), np.nan) for n in ("dq", "dk", "dv")}
     for u in range(nu):
         for k in range(4):                                           # S^T_u = K_u Q^T, dP^T_u = V_u dO^T
             tm.umma(TMB_S, SP, sm.read_k_major(sK + u * 16384 + k * 32, 1024, 128), sm.read_k_major(sQ + k * 32, 1024, SP), k > 0)
         for k in range(4):
             tm.umma(TMB_DP, SP, sm.read_k_major(sV + u * 16384 + k * 32, 1024, 128), sm.read_k_major(sdO + k * 32, 1024, SP), k > 0)
-        for q in range(4):                                           # element-wise warps (q, half), lane = key row
+        for q in range(4):                                           # element-wise warps (q, part), lane = key row
             if u * 128 + q * 32 >= S:
                 continue
             keys = u * 128 + q * 32 + np.arange(32)
             bias = np.where(keys < S, np.where(np.pad(mask, (0, 256))[keys] != 0, np.float32(0), MASK_LOG2),
                             np.float32(-np.inf)).astype(np.float32)
-            for half in range(2):
-                c0, c1 = (0, csplit) if half == 0 else (csplit, SP)
+            for part in range(nsplit):
+                c0, c1 = min(part * per, nch) * 16, min((part + 1) * per, nch) * 16
                 for c in range(c0, c1, 16):
                     s, dp = tm.ld(q, TMB_S + c, 16), tm.ld(q, TMB_DP + c, 16)
                     p = np.exp2((s * SCALE_LOG2 + bias[:, None]) - lse2[None, c:c + 16]).astype(np.float32)
@@ -175,28 +176,31 @@ def backward_walk(S, SP, Q, K, V, dO, ctx, lse, mask, thresh, scale, hkey):
             for kk in range(ksteps):
                 tm.umma(TMB_DQ + 64 * m, HD, sm.read_mn_major(off_ds + m * 2 * P_CHUNK + kk * 2048, P_CHUNK, 1024, 128),
                         sm.read_mn_major(sK + u * 16384 + kk * 2048, 8192, 1024, HD), u > 0 or kk > 0)
-        for q in range(4):                                           # dV_u (half 0) / dK_u (half 1) -> dqkv
+        for q in range(4):                                           # [dV_u | dK_u] -> dqkv
             if u * 128 + q * 32 >= S:
                 continue
-            for half, name, col in ((0, "dv", TMB_DV), (1, "dk", TMB_DK)):
-                o = tm.ld(q, col, HD)
+            wkv = 128 // nsplit                                      # part -> slice of TMEM columns [dV | dK] = [0,128)
+            for part in range(nsplit):
+                ckv = part * wkv
+                o = tm.ld(q, TMB_DV + ckv, wkv)
                 for lane in range(32):
                     key = u * 128 + q * 32 + lane
                     if key < S:
-                        dqkv[name][key] = bf(o[lane])
-    for q in range(4):                                               # dQ epilogue: half = 32 of the 64 columns
+                        dqkv["dv" if ckv < HD else "dk"][key, ckv & (HD - 1):(ckv & (HD - 1)) + wkv] = bf(o[lane])
+    for q in range(4):                                               # dQ epilogue: part = 64 / nsplit of the 64 columns
         if q * 32 >= S:
             continue
-        for half in range(2):
-            o = tm.ld(q, TMB_DQ + half * 32, 32)
+        wq = HD // nsplit
+        for part in range(nsplit):
+            o = tm.ld(q, TMB_DQ + part * wq, wq)
             for lane in range(32):
                 if q * 32 + lane < S:
-                    dqkv["dq"][q * 32 + lane, half * 32:half * 32 + 32] = bf(o[lane])
+                    dqkv["dq"][q * 32 + lane, part * wq:(part + 1) * wq] = bf(o[lane])
             if nu == 2 and q == 0:
-                o = tm.ld(0, TMB_DQ + 64 + half * 32, 32)
+                o = tm.ld(0, TMB_DQ + 64 + part * wq, wq)
                 for lane in range(32):
                     if 128 + lane < S:
-                        dqkv["dq"][128 + lane, half * 32:half * 32 + 32] = bf(o[lane])
+                        dqkv["dq"][128 + lane, part * wq:(part + 1) * wq] = bf(o[lane])
     return dqkv["dq"], dqkv["dk"], dqkv["dv"]
 
 
@@ -208,7 +212,8 @@ def test_forward_and_backward_dataflow(S, p_drop):
     assert np.isfinite(ctx).all() and np.isfinite(lse).all()
     assert np.abs(ctx - O).max() <= 2e-2                                  # north_star: hidden states 2e-2 abs (bf16)
     assert np.abs(lse - lse_ref).max() <= 2e-3
-    dq, dk, dv = backward_walk(S, SP, Q, K, V, dO, ctx, lse, mask, thresh, scale, hkey)
-    for got, ref, name in ((dq, dQ, "dQ"), (dk, dK, "dK"), (dv, dV, "dV")):
-        assert np.isfinite(got).all(), name
-        assert np.abs(got - ref).max() <= 1.5e-2 * max(np.abs(dQ).max(), np.abs(dK).max(), np.abs(dV).max()), name
+    for nsplit in (2, 4):
+        dq, dk, dv = backward_walk(S, SP, Q, K, V, dO, ctx, lse, mask, thresh, scale, hkey, nsplit)
+        for got, ref, name in ((dq, dQ, "dQ"), (dk, dK, "dK"), (dv, dV, "dV")):
+            assert np.isfinite(got).all(), (name, nsplit)
+            assert np.abs(got - ref).max() <= 1.5e-2 * max(np.abs(dQ).max(), np.abs(dK).max(), np.abs(dV).max()), (name, nsplit)

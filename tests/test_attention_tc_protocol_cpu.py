@@ -159,9 +159,9 @@ def forward_protocol(S, items, rng):
 
 
 # ------------------------------------------------------------------------------------------- backward
-def backward_protocol(S, items, rng):
+def backward_protocol(S, items, rng, nsplit=2):
     nu = 2 if S > 128 else 1
-    na = [2 * active_warps(S, u) for u in range(2)]          # two column halves per active lane quarter
+    na = [nsplit * active_warps(S, u) for u in range(2)]     # nsplit column parts per active lane quarter
     ld_full, ld_empty = MBar(1), MBar(1)
     sd_full = [MBar(1), MBar(1)]
     pds_full = [MBar(max(na[u], 1)) for u in range(2)]
@@ -174,8 +174,8 @@ def backward_protocol(S, items, rng):
     pds = Resource("Pd^T,dS^T", 0, 2)                         # dV/dK MMAs and dQ MMAs
     dvk = Resource("dV,dK", 1, 0)
     dq = Resource("dQ", nu, na[0])
-    vecs = [Resource(f"lse2/delta[{b}]", 8, sum(na[:nu])) for b in range(2)]
-    group = {"count": 0, "gen": 0}                            # bar.sync 1, 256 among the eight element-wise warps
+    vecs = [Resource(f"lse2/delta[{b}]", 4 * nsplit, sum(na[:nu])) for b in range(2)]
+    group = {"count": 0, "gen": 0}                            # bar.sync 1, 128 * nsplit among the element-wise warps
     done = []
 
     def producer():
@@ -230,7 +230,7 @@ def backward_protocol(S, items, rng):
             yield None
             gen = group["gen"]                                # bar.sync 1, 256
             group["count"] += 1
-            if group["count"] == 8:
+            if group["count"] == 4 * nsplit:
                 group["count"] = 0
                 group["gen"] += 1
             while group["gen"] == gen:
@@ -257,9 +257,9 @@ def backward_protocol(S, items, rng):
                 dq_empty.arrive()
             done.append((it, q, half))
 
-    actors = [producer(), mma()] + [elementwise(q, h) for q in range(4) for h in range(2)]
+    actors = [producer(), mma()] + [elementwise(q, h) for q in range(4) for h in range(nsplit)]
     run(actors, [tma, pipe], rng)
-    assert len(done) == items * 8
+    assert len(done) == items * 4 * nsplit
 
 
 @pytest.mark.parametrize("S", [160, 145, 129, 128, 100, 97, 96, 76, 65, 33, 16, 1])
@@ -270,8 +270,9 @@ def test_forward_protocol(S, seed):
 
 @pytest.mark.parametrize("S", [160, 145, 129, 128, 100, 97, 96, 76, 65, 33, 16, 1])
 @pytest.mark.parametrize("seed", range(6))
-def test_backward_protocol(S, seed):
-    backward_protocol(S, items=7, rng=random.Random(1000 * S + seed))
+@pytest.mark.parametrize("nsplit", [2, 4])
+def test_backward_protocol(S, seed, nsplit):
+    backward_protocol(S, items=7, rng=random.Random(1000 * S + seed), nsplit=nsplit)
 
 
 def test_simulator_catches_a_missing_wait():

@@ -365,48 +365,32 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int S, int SP) {
 
 constexpr uint32_t TMB_S = 0, TMB_DP = 192, TMB_DV = 0, TMB_DK = 64, TMB_DQ = 384;
 
-// 64 accumulator columns of this thread's row, scaled, -> 64 bf16 at dst
-__device__ __forceinline__ void store_row64(uint32_t taddr, bf16* dst, bool ok) {
-    uint32_t r[32];
+// W (16, 32 or 64) accumulator columns of this thread's row -> W bf16 at dst
+template <int W>
+__device__ __forceinline__ void store_cols(uint32_t taddr, bf16* dst, bool ok) {
+    uint32_t r[16];
 #pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-        ptx::tmem_ld_32x32(taddr + c, r);
+    for (int c = 0; c < W; c += 16) {
+        ptx::tmem_ld_32x16(taddr + c, r);
         ptx::tmem_wait_ld();
-        if (ok) {
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-                ptx::stg256(dst + c + 16 * g,
-                            pack_bf16(__uint_as_float(r[16 * g + 0]), __uint_as_float(r[16 * g + 1])),
-                            pack_bf16(__uint_as_float(r[16 * g + 2]), __uint_as_float(r[16 * g + 3])),
-                            pack_bf16(__uint_as_float(r[16 * g + 4]), __uint_as_float(r[16 * g + 5])),
-                            pack_bf16(__uint_as_float(r[16 * g + 6]), __uint_as_float(r[16 * g + 7])),
-                            pack_bf16(__uint_as_float(r[16 * g + 8]), __uint_as_float(r[16 * g + 9])),
-                            pack_bf16(__uint_as_float(r[16 * g + 10]), __uint_as_float(r[16 * g + 11])),
-                            pack_bf16(__uint_as_float(r[16 * g + 12]), __uint_as_float(r[16 * g + 13])),
-                            pack_bf16(__uint_as_float(r[16 * g + 14]), __uint_as_float(r[16 * g + 15])));
-        }
-    }
-}
-__device__ __forceinline__ void store_row32(uint32_t taddr, bf16* dst, bool ok) {
-    uint32_t r[32];
-    ptx::tmem_ld_32x32(taddr, r);
-    ptx::tmem_wait_ld();
-    if (ok) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-            ptx::stg256(dst + 16 * g,
-                        pack_bf16(__uint_as_float(r[16 * g + 0]), __uint_as_float(r[16 * g + 1])),
-                        pack_bf16(__uint_as_float(r[16 * g + 2]), __uint_as_float(r[16 * g + 3])),
-                        pack_bf16(__uint_as_float(r[16 * g + 4]), __uint_as_float(r[16 * g + 5])),
-                        pack_bf16(__uint_as_float(r[16 * g + 6]), __uint_as_float(r[16 * g + 7])),
-                        pack_bf16(__uint_as_float(r[16 * g + 8]), __uint_as_float(r[16 * g + 9])),
-                        pack_bf16(__uint_as_float(r[16 * g + 10]), __uint_as_float(r[16 * g + 11])),
-                        pack_bf16(__uint_as_float(r[16 * g + 12]), __uint_as_float(r[16 * g + 13])),
-                        pack_bf16(__uint_as_float(r[16 * g + 14]), __uint_as_float(r[16 * g + 15])));
+        if (ok)
+            ptx::stg256(dst + c, pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])),
+                        pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])),
+                        pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5])),
+                        pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7])),
+                        pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9])),
+                        pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11])),
+                        pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])),
+                        pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15])));
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NSPLIT element-wise warps share a TMEM lane quarter (2: 8 warps, 4: 16 warps = four per scheduler; the loops
+// are bound by instruction issue and latency, like the GELU epilogues of the GEMM that run 16 warps for this reason)
+__host__ __device__ constexpr int bwd_threads(int nsplit) { return 64 + 128 * nsplit; }
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(bwd_threads(NSPLIT), 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                         const TcBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -434,14 +418,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         ptx::mbar_init(ld_full, 1);
         ptx::mbar_init(ld_empty, 1);
         for (int u = 0; u < 2; ++u) {
-            const int na = 2 * active_warps(S, u);            // two column halves per active lane quarter
+            const int na = NSPLIT * active_warps(S, u);       // NSPLIT column parts per active lane quarter
             ptx::mbar_init(sd_full(u), 1);
             ptx::mbar_init(pds_full(u), na > 0 ? na : 1);
             ptx::mbar_init(kv_full(u), 1);
             ptx::mbar_init(s_empty(u), na > 0 ? na : 1);
         }
         ptx::mbar_init(dq_full, 1);
-        ptx::mbar_init(dq_empty, 2 * active_warps(S, 0));
+        ptx::mbar_init(dq_empty, NSPLIT * active_warps(S, 0));
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
@@ -530,13 +514,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     } else {
         // ===================================== element-wise warps ============================
         const int q = warp & 3;                         // TMEM lane quarter
-        const int half = (warp - 2) >> 2;               // which half of the query columns / of the outputs
+        const int part = (warp - 2) >> 2;               // which part of the query columns / of the outputs
         const int ew = warp - 2;
         const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
         const int kr = q * 32 + lane;                   // row inside a 128-row tile
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
-        const int csplit = ((SP / 16 + 1) / 2) * 16;
-        const int c_begin = half == 0 ? 0 : csplit, c_end = half == 0 ? csplit : SP;
+        const int nch = SP / 16, per = (nch + NSPLIT - 1) / NSPLIT;          // 16-column chunks per part
+        const int c_begin = min(part * per, nch) * 16, c_end = min((part + 1) * per, nch) * 16;
         int it = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
             const uint32_t itp = it & 1u;
@@ -547,8 +531,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             float* delta = lse2 + SP;
             {
                 const float* Lg = p.lse + ((long long)b * NH + h) * S;
-                for (int i = threadIdx.x - 64; i < SP; i += 256) lse2[i] = i < S ? Lg[i] * LOG2E : INFINITY;
-                for (int r0 = ew * 4; r0 < SP; r0 += 32) {
+                for (int i = threadIdx.x - 64; i < SP; i += 128 * NSPLIT) lse2[i] = i < S ? Lg[i] * LOG2E : INFINITY;
+                for (int r0 = ew * 4; r0 < SP; r0 += 16 * NSPLIT) {
                     const int r = r0 + (lane >> 3), c8 = (lane & 7) * 8;
                     float acc = 0.f;
                     if (r < S) {
@@ -564,7 +548,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                     if ((lane & 7) == 0 && r < SP) delta[r] = acc;
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");         // the eight element-wise warps only
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * NSPLIT) : "memory");   // the element-wise warps only
             const uint32_t hkey = drop_head_key(p.drop.key, b * NH + h);
 
             for (int u = 0; u < nu; ++u) {
@@ -611,25 +595,28 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(pds_full(u));
 
-                // dV_u (half 0) / dK_u (half 1) of this key row -> dqkv
+                // this key row's [dV_u | dK_u] = TMEM columns [0,128): part -> a 128 / NSPLIT-column slice -> dqkv
                 ptx::mbar_wait(kv_full(u), itp);
                 ptx::tc_fence_after();
-                bf16* dst = p.dqkv + (row0 + key) * QKV_LD + (half == 0 ? 2 * HID : HID) + h * HD;
-                store_row64(tmem_base + lane_sel + (half == 0 ? TMB_DV : TMB_DK), dst, key_ok);
+                constexpr int WKV = 128 / NSPLIT;
+                const int ckv = part * WKV;
+                bf16* dst = p.dqkv + (row0 + key) * QKV_LD + (ckv < HD ? 2 * HID : HID) + h * HD + (ckv & (HD - 1));
+                store_cols<WKV>(tmem_base + lane_sel + TMB_DV + ckv, dst, key_ok);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(s_empty(u));
             }
 
-            // dQ: query rows in the lanes; half = which 32 of the 64 columns
+            // dQ: query rows in the lanes; part = which 64 / NSPLIT of the 64 columns
             if (q * 32 < S) {
                 ptx::mbar_wait(dq_full, itp);
                 ptx::tc_fence_after();
-                store_row32(tmem_base + lane_sel + TMB_DQ + half * 32, p.dqkv + (row0 + kr) * QKV_LD + h * HD + half * 32,
-                            kr < S);
+                constexpr int WQ = HD / NSPLIT;
+                store_cols<WQ>(tmem_base + lane_sel + TMB_DQ + part * WQ,
+                               p.dqkv + (row0 + kr) * QKV_LD + h * HD + part * WQ, kr < S);
                 if (nu == 2 && q == 0)
-                    store_row32(tmem_base + TMB_DQ + 64u + half * 32,
-                                p.dqkv + (row0 + 128 + lane) * QKV_LD + h * HD + half * 32, 128 + lane < S);
+                    store_cols<WQ>(tmem_base + TMB_DQ + 64u + part * WQ,
+                                   p.dqkv + (row0 + 128 + lane) * QKV_LD + h * HD + part * WQ, 128 + lane < S);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(dq_empty);
@@ -730,9 +717,14 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     const TcBwdSmem L = tc_bwd_smem(S, SP);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
+    static int nsplit = 2;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(tc_bwd_smem(TC_MAX_SP, TC_MAX_SP).total));
+        const char* e = getenv("UC2_ATTN_TC_BWD_SPLIT");          // tuning knob: 2 (default) or 4 warps per lane quarter
+        if (e && e[0] == '4') nsplit = 4;
+        const int bytes = static_cast<int>(tc_bwd_smem(TC_MAX_SP, TC_MAX_SP).total);
+        attr_err = cudaFuncSetAttribute(attention_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attention_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     });
     UC2_REQUIRE(attr_err == cudaSuccess, UC2_ERR_CUDA, "attention_bwd_tc: cudaFuncSetAttribute failed: %s",
                 cudaGetErrorString(attr_err));
@@ -746,8 +738,11 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     p.drop = DropCfg{drop_key, drop_thresh, drop_scale};
     const int grid = p.items < num_sms() ? p.items : num_sms();
     ProfScope prof((cudaStream_t)stream, 1, 10.0 * B * NH * (double)S * S * HD);
-    const cudaError_t e = launch_pdl(attention_bwd_tc_kernel, dim3(grid), dim3(TC_THREADS), exclusive_smem(L.total),
-                                     (cudaStream_t)stream, 1, tq, tdo, p);
+    const cudaError_t e =
+        nsplit == 4 ? launch_pdl(attention_bwd_tc_kernel<4>, dim3(grid), dim3(bwd_threads(4)), exclusive_smem(L.total),
+                                 (cudaStream_t)stream, 1, tq, tdo, p)
+                    : launch_pdl(attention_bwd_tc_kernel<2>, dim3(grid), dim3(bwd_threads(2)), exclusive_smem(L.total),
+                                 (cudaStream_t)stream, 1, tq, tdo, p);
     UC2_REQUIRE(e == cudaSuccess, UC2_ERR_CUDA, "attention_bwd_tc launch failed: %s", cudaGetErrorString(e));
     return check_last("attention_bwd_tc_kernel");
 }
