@@ -159,7 +159,7 @@ def backward_walk(S, SP, Q, K, V, dO, ctx, lse, mask, thresh, scale, hkey, nspli
                         idx = (c + np.arange(16))[None, :].astype(np.uint64) * S + keys[:, None]
                         kp = DR.keep_mask_np(hkey, None, thresh, idx)
                         pd, dp = np.where(kp, p * scale, np.float32(0)), np.where(kp, dp * scale, np.float32(0))
-                    ds = p * (dp - delta[None, c:c + 16]) * np.float32(0.125)
+                    ds = p * (dp - delta[None, c:c + 16])            # the 1/8 is applied in the dK / dQ epilogues
                     pdb, dsb = bf(pd), bf(ds)
                     for lane in range(32):
                         for g in range(2):
@@ -186,7 +186,8 @@ def backward_walk(S, SP, Q, K, V, dO, ctx, lse, mask, thresh, scale, hkey, nspli
                 for lane in range(32):
                     key = u * 128 + q * 32 + lane
                     if key < S:
-                        dqkv["dv" if ckv < HD else "dk"][key, ckv & (HD - 1):(ckv & (HD - 1)) + wkv] = bf(o[lane])
+                        dqkv["dv" if ckv < HD else "dk"][key, ckv & (HD - 1):(ckv & (HD - 1)) + wkv] = \
+                            bf(o[lane] * np.float32(1.0 if ckv < HD else 0.125))
     for q in range(4):                                               # dQ epilogue: part = 64 / nsplit of the 64 columns
         if q * 32 >= S:
             continue
@@ -195,12 +196,12 @@ def backward_walk(S, SP, Q, K, V, dO, ctx, lse, mask, thresh, scale, hkey, nspli
             o = tm.ld(q, TMB_DQ + part * wq, wq)
             for lane in range(32):
                 if q * 32 + lane < S:
-                    dqkv["dq"][q * 32 + lane, part * wq:(part + 1) * wq] = bf(o[lane])
+                    dqkv["dq"][q * 32 + lane, part * wq:(part + 1) * wq] = bf(o[lane] * np.float32(0.125))
             if nu == 2 and q == 0:
                 o = tm.ld(0, TMB_DQ + 64 + part * wq, wq)
                 for lane in range(32):
                     if 128 + lane < S:
-                        dqkv["dq"][128 + lane, part * wq:(part + 1) * wq] = bf(o[lane])
+                        dqkv["dq"][128 + lane, part * wq:(part + 1) * wq] = bf(o[lane] * np.float32(0.125))
     return dqkv["dq"], dqkv["dk"], dqkv["dv"]
 
 

@@ -329,9 +329,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const TcPa
 // memory, the key's mask bias is a per-thread scalar) and both halves of the query columns of a key row can go to
 // two different warps.  Per (batch, head) item and key tile u (128 keys; u = 1 holds keys 128..159):
 //     S^T_u = K_u Q^T, dP^T_u = V_u dO^T                                   (M 128, N SP, K 64; TMEM [0,160) [192,352))
-//     element-wise: P = exp2(s - lse), dropout, dS = P (dP - delta) / 8   -> Pd^T_u, dS^T_u as bf16 K-major tiles
-//     dV_u = Pd^T_u dO, dK_u = dS^T_u Q                                    (M 128, N 64, K SP; alias TMEM [0,64) [64,128))
-//     dQ_m += dS_u K_u  for the query tiles m                             (A = the dS^T tile read MN-major; TMEM [384,512))
+//     element-wise: P = exp2(s - lse), dropout, dS = P (dP - delta)       -> Pd^T_u, dS^T_u as bf16 K-major tiles
+//     dV_u = Pd^T_u dO, dK_u = dS^T_u Q / 8                                (M 128, N 64, K SP; alias TMEM [0,64) [64,128))
+//     dQ_m += dS_u K_u / 8  for the query tiles m                         (A = the dS^T tile read MN-major; TMEM [384,512))
 // Tiles of Q, K, V, dO come by TMA once per item (single buffered: the next item's loads fly under this item's
 // last epilogues); 8 element-wise warps = 4 TMEM lane quarters x 2 column halves.
 // =================================================================================================
@@ -365,23 +365,21 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int S, int SP) {
 
 constexpr uint32_t TMB_S = 0, TMB_DP = 192, TMB_DV = 0, TMB_DK = 64, TMB_DQ = 384;
 
-// W (16, 32 or 64) accumulator columns of this thread's row -> W bf16 at dst
+// W (16, 32 or 64) accumulator columns of this thread's row, times `scale`, -> W bf16 at dst
 template <int W>
-__device__ __forceinline__ void store_cols(uint32_t taddr, bf16* dst, bool ok) {
+__device__ __forceinline__ void store_cols(uint32_t taddr, bf16* dst, bool ok, float scale) {
     uint32_t r[16];
 #pragma unroll
     for (int c = 0; c < W; c += 16) {
         ptx::tmem_ld_32x16(taddr + c, r);
         ptx::tmem_wait_ld();
-        if (ok)
-            ptx::stg256(dst + c, pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])),
-                        pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])),
-                        pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5])),
-                        pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7])),
-                        pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9])),
-                        pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11])),
-                        pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])),
-                        pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15])));
+        if (ok) {
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                o[j] = pack_bf16(__uint_as_float(r[2 * j]) * scale, __uint_as_float(r[2 * j + 1]) * scale);
+            ptx::stg256(dst + c, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+        }
     }
 }
 
@@ -580,7 +578,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                             pd1 = k1 ? p1 * p.drop.scale : 0.f; dp1 = k1 ? dp1 * p.drop.scale : 0.f;
                         }
                         pd[j / 2] = pack_bf16(pd0, pd1);
-                        ds[j / 2] = pack_bf16(p0 * (dp0 - de.x) * 0.125f, p1 * (dp1 - de.y) * 0.125f);
+                        // dS without the 1/sqrt(64): a power of two commutes with the bf16 rounding, so it is applied
+                        // once per OUTPUT element in the dK / dQ epilogues instead of once per score here
+                        ds[j / 2] = pack_bf16(p0 * (dp0 - de.x), p1 * (dp1 - de.y));
                     }
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
@@ -601,7 +601,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 constexpr int WKV = 128 / NSPLIT;
                 const int ckv = part * WKV;
                 bf16* dst = p.dqkv + (row0 + key) * QKV_LD + (ckv < HD ? 2 * HID : HID) + h * HD + (ckv & (HD - 1));
-                store_cols<WKV>(tmem_base + lane_sel + TMB_DV + ckv, dst, key_ok);
+                store_cols<WKV>(tmem_base + lane_sel + TMB_DV + ckv, dst, key_ok, ckv < HD ? 1.f : 0.125f);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(s_empty(u));
@@ -613,10 +613,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 ptx::tc_fence_after();
                 constexpr int WQ = HD / NSPLIT;
                 store_cols<WQ>(tmem_base + lane_sel + TMB_DQ + part * WQ,
-                               p.dqkv + (row0 + kr) * QKV_LD + h * HD + part * WQ, kr < S);
+                               p.dqkv + (row0 + kr) * QKV_LD + h * HD + part * WQ, kr < S, 0.125f);
                 if (nu == 2 && q == 0)
                     store_cols<WQ>(tmem_base + TMB_DQ + 64u + part * WQ,
-                                   p.dqkv + (row0 + 128 + lane) * QKV_LD + h * HD + part * WQ, 128 + lane < S);
+                                   p.dqkv + (row0 + 128 + lane) * QKV_LD + h * HD + part * WQ, 128 + lane < S, 0.125f);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(dq_empty);
