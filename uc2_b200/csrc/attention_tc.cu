@@ -574,8 +574,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                             const uint32_t i0 = static_cast<uint32_t>(c + j) * static_cast<uint32_t>(S) + key;
                             const bool k0 = drop_keep(hkey, i0, p.drop.thresh);
                             const bool k1 = drop_keep(hkey, i0 + static_cast<uint32_t>(S), p.drop.thresh);
-                            pd0 = k0 ? p0 * p.drop.scale : 0.f; dp0 = k0 ? dp0 * p.drop.scale : 0.f;
-                            pd1 = k1 ? p1 * p.drop.scale : 0.f; dp1 = k1 ? dp1 * p.drop.scale : 0.f;
+                            const float s0 = k0 ? p.drop.scale : 0.f, s1 = k1 ? p.drop.scale : 0.f;   // finite operands only
+                            pd0 = p0 * s0; dp0 *= s0;
+                            pd1 = p1 * s1; dp1 *= s1;
                         }
                         pd[j / 2] = pack_bf16(pd0, pd1);
                         // dS without the 1/sqrt(64): a power of two commutes with the bf16 rounding, so it is applied
