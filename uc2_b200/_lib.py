@@ -177,6 +177,11 @@ def attention_tc_enabled():
     return bool(prev)
 
 
+def attention_kernels(S):
+    """Which attention kernels the public entry points run for a packed length S (for the bench line)."""
+    return "tcgen05/TMEM (attention_tc.cu)" if attention_tc_enabled() and S <= 160 else "mma.sync (attention.cu)"
+
+
 def launch_count():
     return int(lib().uc2_launch_count())
 
