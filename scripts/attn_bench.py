@@ -28,6 +28,10 @@ for B, S in [(120, 160), (8, 76), (48, 220), (5, 300), (7, 33)]:
     delta = torch.empty(B, 12, S, device=dev)
     f = lambda: call("uc2_attention_fwd", qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, stream())
     bw = lambda: call("uc2_attention_bwd", qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, S, stream())
+    drop = (0x1234567, int(round(0.1 * 65536)), 1.0 / 0.9)
+    fd = lambda: call("uc2_attention_fwd_dropout", qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, S, *drop, stream())
+    bd = lambda: call("uc2_attention_bwd_dropout", qkv.data_ptr(), mask.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, S, *drop, stream())
+    ufd = t(fd) if S <= 256 else float("nan"); ubd = t(bd) if S <= 256 else float("nan")
     uf = t(f); ub = t(bw)
     fl = 4.0 * B * 12 * S * S * 64
     # reference
@@ -41,4 +45,4 @@ for B, S in [(120, 160), (8, 76), (48, 220), (5, 300), (7, 33)]:
     e_f = (ctx.float() - o).abs().max().item()
     e_b = (dqkv.float() - gref).abs().max().item() / gref.abs().max().item()
     print(f"B={B:4d} S={S:4d}  fwd {uf:7.1f} us {fl / uf / 1e6:6.1f} TFLOP/s   bwd {ub:7.1f} us {2.5 * fl / ub / 1e6:6.1f} TFLOP/s (5 products)   "
-          f"max err fwd {e_f:.4f} bwd rel {e_b:.4f}")
+          f"max err fwd {e_f:.4f} bwd rel {e_b:.4f}   with dropout 0.1: fwd {ufd:7.1f} us bwd {ubd:7.1f} us")

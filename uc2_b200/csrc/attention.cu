@@ -856,7 +856,7 @@ extern "C" UC2_API int uc2_attention_fwd_dropout(const void* qkv, const long lon
     int S_pad;
     if (int rc = attn_check(B, S, &S_pad)) return rc;
     // opt-in tcgen05 / TMEM forward (attention_tc.cu), same results by construction; off unless enabled
-    if (attn_tc_enabled() && S <= 160 && (reinterpret_cast<uintptr_t>(ctx) & 31) == 0)
+    if (attn_tc_enabled() && S <= 256 && (reinterpret_cast<uintptr_t>(ctx) & 31) == 0)
         return uc2_attention_fwd_tc(qkv, attn_mask, ctx, lse, B, S, drop_key, drop_thresh, drop_scale, stream);
     ProfScope prof((cudaStream_t)stream, 1, 4.0 * B * NH * (double)S * S * HD);
     if (S <= 256) {

@@ -36,14 +36,14 @@ namespace {
 constexpr int HD = 64;
 constexpr int NH = 12;
 constexpr int QKV_LD = 3 * HID;
-constexpr int TC_MAX_SP = 160;
-constexpr int TC_THREADS = 320;              // TMA warp, MMA warp, 2 x 4 softmax warps
+constexpr int TC_MAX_SP = 256;               // forward; the backward kernel below stops at TC_BWD_MAX_SP
+constexpr int FWD_NSPLIT = 2;                // softmax warps per TMEM lane quarter (each takes a column range of the row)
+constexpr int FWD_EW = 4 * FWD_NSPLIT;
+constexpr int FWD_THREADS = 64 + 32 * FWD_EW;   // TMA warp, MMA warp, the softmax warps
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float SCALE_LOG2 = 0.125f * LOG2E;
 constexpr float MASK_LOG2 = -10000.0f * LOG2E;
-// accumulator column bases kept on multiples of 64 (the 160-column S tiles get 192-column slots)
-constexpr uint32_t TM_S = 0, TM_S_STRIDE = 192, TM_O = 384, TM_O_STRIDE = 64, TMEM_COLS = 512;
-constexpr uint32_t P_CHUNK_BYTES = 128 * 128;   // 128 query rows x 64 keys of bf16
+constexpr uint32_t P_CHUNK_BYTES = 128 * 128;   // 128 rows x 64 columns of bf16 (the backward's K-major operand tiles)
 
 struct TcParams {
     const long long* mask;
@@ -51,23 +51,57 @@ struct TcParams {
     float* lse;
     int B, S, SP, items;
     DropCfg drop;
+    long long* prof;      // debug (UC2_ATTN_PROF=1): per CTA, per warp, 8 cycle counters; nullptr otherwise
+};
+constexpr int PROF_SLOTS = 8;
+struct PhaseClock {       // accumulates clock64 deltas of one warp's phases when profiling is on
+    long long* out;
+    long long t;
+    __device__ __forceinline__ PhaseClock(long long* base, int warps_per_cta) {
+        out = base ? base + ((long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5)) * PROF_SLOTS : nullptr;
+        t = out ? clock64() : 0;
+    }
+    __device__ __forceinline__ void lap(int slot) {
+        if (out) {
+            const long long now = clock64();
+            if ((threadIdx.x & 31) == 0) out[slot] += now - t;
+            t = now;
+        }
+    }
 };
 
-// shared-memory plan shared by host and device
+// shared-memory / tensor-memory plan shared by host and device
 struct TcSmem {
-    uint32_t tile_bytes, buf_bytes, p_tile_bytes, off_p, off_mbias, off_bar, total;
-    int nt, nchunk;
+    uint32_t tile_bytes, off_q1, off_kv, off_mbias, off_info, off_red, off_bar, total;
+    uint32_t tm_cols, tm_o;
+    int nt, rem, rot_step, rot_n;
 };
 __host__ __device__ inline TcSmem tc_smem(int S, int SP) {
     TcSmem L;
     L.nt = S > 128 ? 2 : 1;
-    L.nchunk = (SP + 63) >> 6;
     L.tile_bytes = SP * 128u;
-    L.buf_bytes = 3u * L.tile_bytes;
-    L.p_tile_bytes = L.nchunk * P_CHUNK_BYTES;
-    L.off_p = 2u * L.buf_bytes;
-    L.off_mbias = L.off_p + L.nt * L.p_tile_bytes;
-    L.off_bar = L.off_mbias + 2u * SP * 4u;
+    // SP <= 160: 256 columns per CTA (S [0,160), O [160,224)) and two CTAs per SM; above: all 512 columns (S [0,256),
+    // O [256,320)) and the SM to itself.  P overwrites S in place: a softmax warp owns the column range [c0, c1) of
+    // its rows and stores the bf16 pairs of keys c.. at columns c0 + (c - c0) / 2, which it has already read.
+    const bool small = SP <= 160;
+    L.tm_cols = small ? 256u : 512u;
+    L.tm_o = small ? 160u : 256u;
+    // [Q rows 0..127 (16 KB)] [Q rows 128..SP-1] [K0 V0] [K1 V1]: Q single buffered (dead once the item's S products
+    // retire), K / V double buffered.  The M = 128 reads of a Q tile cover 16 KB whatever SP is; what lies past the
+    // valid rows is other tiles' data and lands in accumulator lanes nobody reads.
+    // The remainder tile (rows 128..) holds `rem` valid rows.  A warp can only read the TMEM lane quarter warp % 4,
+    // which is also its scheduler, so with the remainder always in lanes 0.. one scheduler would do twice the
+    // softmax work of the others: the tile's base address is shifted down by rot rows instead (rot = rot_step *
+    // ((item counter + CTA) % rot_n)), which moves the valid rows to lanes rot.. and spreads that work over time.
+    L.rem = L.nt == 2 ? SP - 128 : 0;
+    L.rot_step = L.rem <= 32 ? 32 : 64;
+    L.rot_n = L.nt == 2 ? (L.rem <= 32 ? 4 : (L.rem <= 64 ? 2 : 1)) : 1;
+    L.off_q1 = 16384u;
+    L.off_kv = L.off_q1 + L.rem * 128u;
+    L.off_mbias = L.off_kv + 4u * L.tile_bytes;
+    L.off_info = L.off_mbias + 2u * SP * 4u;
+    L.off_red = L.off_info + 32u;
+    L.off_bar = L.off_red + FWD_EW * 32u * 8u;
     L.total = 1024u + L.off_bar + 128u;
     return L;
 }
@@ -77,68 +111,165 @@ __host__ __device__ inline int active_warps(int S, int t) {
     return rows <= 0 ? 0 : (rows >= 128 ? 4 : (rows + 31) >> 5);
 }
 
-// One pass-2 chunk: NC (16 or 32) score columns of this thread's row -> probabilities -> bf16 into the P tile
-template <int NC>
-__device__ __forceinline__ void softmax_chunk(const uint32_t* r, const float* mb, int c, float m, float& l,
-                                              const DropCfg& drop, uint32_t hkey, uint32_t row_idx0, uint32_t prow,
-                                              uint32_t sw) {
-    uint32_t pk[NC / 2];
+// Pass 1 over 16 score columns of this thread's row.  PREFIX: every one of the 16 keys is valid (bias 0), the
+// maximum is taken on the raw scores and scaled once per row; else the additive bias row is applied per element.
+template <bool PREFIX>
+__device__ __forceinline__ float max_chunk16(const uint32_t* r, const float* mb, float m) {
+    if (PREFIX) {
 #pragma unroll
-    for (int j = 0; j < NC; j += 4) {
-        const float4 bb = *reinterpret_cast<const float4*>(mb + c + j);
-        float p0 = fast_ex2(fmaf(__uint_as_float(r[j]), SCALE_LOG2, bb.x) - m);
-        float p1 = fast_ex2(fmaf(__uint_as_float(r[j + 1]), SCALE_LOG2, bb.y) - m);
-        float p2 = fast_ex2(fmaf(__uint_as_float(r[j + 2]), SCALE_LOG2, bb.z) - m);
-        float p3 = fast_ex2(fmaf(__uint_as_float(r[j + 3]), SCALE_LOG2, bb.w) - m);
-        l += (p0 + p1) + (p2 + p3);
-        if (drop.thresh) {
-            // layer.py:94: the normaliser keeps every key, the dropped and rescaled probabilities only enter P.V
-            bool k0, k1, k2, k3;
-            drop_keep2(hkey, row_idx0 + c + j, drop.thresh, k0, k1);
-            drop_keep2(hkey, row_idx0 + c + j + 2, drop.thresh, k2, k3);
-            p0 = k0 ? p0 * drop.scale : 0.f; p1 = k1 ? p1 * drop.scale : 0.f;
-            p2 = k2 ? p2 * drop.scale : 0.f; p3 = k3 ? p3 * drop.scale : 0.f;
+        for (int j = 0; j < 16; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(mb + j);
+            m = fmaxf(m, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), SCALE_LOG2, bb.x),
+                                     fmaf(__uint_as_float(r[j + 1]), SCALE_LOG2, bb.y)),
+                               fmaxf(fmaf(__uint_as_float(r[j + 2]), SCALE_LOG2, bb.z),
+                                     fmaf(__uint_as_float(r[j + 3]), SCALE_LOG2, bb.w))));
         }
-        pk[j / 2] = pack_bf16(p0, p1);
-        pk[j / 2 + 1] = pack_bf16(p2, p3);
-    }
-#pragma unroll
-    for (int g = 0; g < NC / 8; ++g) {
-        const uint32_t key0 = c + 8 * g;                       // 8 keys = one 16-byte unit of the swizzled row
-        const uint32_t addr = prow + (key0 >> 6) * P_CHUNK_BYTES + ((((key0 & 63u) >> 3) ^ sw) << 4);
-        ptx::st_shared_v4(addr, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-    }
-}
-
-template <int NC>
-__device__ __forceinline__ float max_chunk(const uint32_t* r, const float* mb, int c, float m) {
-#pragma unroll
-    for (int j = 0; j < NC; j += 4) {
-        const float4 bb = *reinterpret_cast<const float4*>(mb + c + j);
-        m = fmaxf(m, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), SCALE_LOG2, bb.x),
-                                 fmaf(__uint_as_float(r[j + 1]), SCALE_LOG2, bb.y)),
-                           fmaxf(fmaf(__uint_as_float(r[j + 2]), SCALE_LOG2, bb.z),
-                                 fmaf(__uint_as_float(r[j + 3]), SCALE_LOG2, bb.w))));
     }
     return m;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const TcParams p) {
+// Pass 2 over 16 score columns: probabilities (relative to the row maximum m, exp2 domain), their sum into l, the
+// attention-probability dropout of layer.py:94 (the normaliser keeps every key; the 1 / (1 - p) rescale is applied
+// once per output element in the epilogue), bf16 pairs into 8 columns of the P tile in tensor memory.
+template <bool PREFIX, bool DROP>
+__device__ __forceinline__ void softmax_chunk16(const uint32_t* r, const float* mb, float m, float& l, uint32_t t32,
+                                                uint32_t rbase, uint32_t tP) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+        float p0, p1, p2, p3;
+        if (PREFIX) {
+            p0 = fast_ex2(fmaf(__uint_as_float(r[j]), SCALE_LOG2, -m));
+            p1 = fast_ex2(fmaf(__uint_as_float(r[j + 1]), SCALE_LOG2, -m));
+            p2 = fast_ex2(fmaf(__uint_as_float(r[j + 2]), SCALE_LOG2, -m));
+            p3 = fast_ex2(fmaf(__uint_as_float(r[j + 3]), SCALE_LOG2, -m));
+        } else {
+            const float4 bb = *reinterpret_cast<const float4*>(mb + j);
+            p0 = fast_ex2(fmaf(__uint_as_float(r[j]), SCALE_LOG2, bb.x) - m);
+            p1 = fast_ex2(fmaf(__uint_as_float(r[j + 1]), SCALE_LOG2, bb.y) - m);
+            p2 = fast_ex2(fmaf(__uint_as_float(r[j + 2]), SCALE_LOG2, bb.z) - m);
+            p3 = fast_ex2(fmaf(__uint_as_float(r[j + 3]), SCALE_LOG2, bb.w) - m);
+        }
+        l += (p0 + p1) + (p2 + p3);
+        if (DROP) {      // common.cuh "Attention-probability dropout": rbase = block hash * CA^(query & 15)
+            p0 = rbase * drop_pow(DROP_CB, j) >= t32 ? p0 : 0.f;
+            p1 = rbase * drop_pow(DROP_CB, j + 1) >= t32 ? p1 : 0.f;
+            p2 = rbase * drop_pow(DROP_CB, j + 2) >= t32 ? p2 : 0.f;
+            p3 = rbase * drop_pow(DROP_CB, j + 3) >= t32 ? p3 : 0.f;
+        }
+        pk[j / 2] = pack_bf16(p0, p1);
+        pk[j / 2 + 1] = pack_bf16(p2, p3);
+    }
+    ptx::tmem_st_32x8(tP, pk);
+}
+
+__device__ __forceinline__ void quarter_sync(int q) {      // the FWD_NSPLIT warps that share TMEM lane quarter q
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * FWD_NSPLIT) : "memory");
+}
+
+// One query row's share (columns [c0, c1), multiples of 16) of the two softmax passes.  The TMEM loads are software
+// pipelined: the next 16 columns are in flight while the current 16 are processed (tcgen05.wait::ld waits for all).
+// Columns [0, nfast) are chunks of valid keys only (prefix masks: all of them), the rest go through the bias row.
+template <bool DROP>
+__device__ __forceinline__ void softmax_row(uint32_t tS, const float* mb, int c0, int c1, int nfast,
+                                            float* red_max, float* red_sum, int slot, int q, int lane, uint32_t t32,
+                                            uint32_t hkey, uint32_t row, float& m_out, float& l_out) {
+    // dropout: per-thread factor of the query row; the block hash is taken per 16-column chunk
+    const uint32_t apow = DROP ? drop_pow_rt(DROP_CA, row) : 0u, iblk = row >> 4;
+    auto rbase = [&](int c) { return DROP ? drop_block_hash(hkey, iblk, static_cast<uint32_t>(c) >> 4) * apow : 0u; };
+    const uint32_t tP = tS + c0 - (c0 >> 1);            // + (c >> 1) = c0 + (c - c0) / 2: P in place, behind the reads
+    uint32_t ra[16], rb[16];
+    float m_raw = -INFINITY, m = -INFINITY, l = 0.f;
+    // ---- pass 1
+    if (c0 < c1) {
+        ptx::tmem_ld_32x16(tS + c0, ra);
+        ptx::tmem_wait_ld16(ra);
+        for (int c = c0; c < c1; c += 32) {
+            if (c + 16 < c1) ptx::tmem_ld_32x16(tS + c + 16, rb);
+            if (c + 16 <= nfast) m_raw = max_chunk16<true>(ra, nullptr, m_raw);
+            else m = max_chunk16<false>(ra, mb + c, m);
+            ptx::tmem_wait_ld16(rb);
+            if (c + 16 < c1) {
+                if (c + 32 < c1) ptx::tmem_ld_32x16(tS + c + 32, ra);
+                if (c + 32 <= nfast) m_raw = max_chunk16<true>(rb, nullptr, m_raw);
+                else m = max_chunk16<false>(rb, mb + c + 16, m);
+                ptx::tmem_wait_ld16(ra);
+            }
+        }
+        ptx::tmem_ld_32x16(tS + c0, ra);                  // first chunk of pass 2, in flight across the exchange
+    }
+    m = fmaxf(m, m_raw * SCALE_LOG2);
+    red_max[slot] = m;
+    quarter_sync(q);
+#pragma unroll
+    for (int o = 0; o < FWD_NSPLIT; ++o) m = fmaxf(m, red_max[(o * 4 + q) * 32 + lane]);
+    // ---- pass 2
+    if (c0 < c1) {
+        ptx::tmem_wait_ld16(ra);
+        for (int c = c0; c < c1; c += 32) {
+            if (c + 16 < c1) ptx::tmem_ld_32x16(tS + c + 16, rb);
+            if (c + 16 <= nfast) softmax_chunk16<true, DROP>(ra, nullptr, m, l, t32, rbase(c), tP + (c >> 1));
+            else softmax_chunk16<false, DROP>(ra, mb + c, m, l, t32, rbase(c), tP + (c >> 1));
+            ptx::tmem_wait_ld16(rb);
+            if (c + 16 < c1) {
+                if (c + 32 < c1) ptx::tmem_ld_32x16(tS + c + 32, ra);
+                if (c + 32 <= nfast)
+                    softmax_chunk16<true, DROP>(rb, nullptr, m, l, t32, rbase(c + 16), tP + ((c + 16) >> 1));
+                else
+                    softmax_chunk16<false, DROP>(rb, mb + c + 16, m, l, t32, rbase(c + 16), tP + ((c + 16) >> 1));
+                ptx::tmem_wait_ld16(ra);
+            }
+        }
+    }
+    red_sum[slot] = l;
+    ptx::tmem_wait_st();
+    quarter_sync(q);
+    l = 0.f;
+#pragma unroll
+    for (int o = 0; o < FWD_NSPLIT; ++o) l += red_sum[(o * 4 + q) * 32 + lane];
+    m_out = m;
+    l_out = l;
+}
+
+// Forward.  CTAs loop over (batch, head) items; two CTAs share an SM for SP <= 160, so one CTA's tensor work and
+// barrier latencies run under the other's softmax.  Per item and query tile t (128 rows; t = 1 holds rows 128..SP-1):
+//     warp 0      TMA: K, V (double buffered) and Q (single buffered: it is dead once the item's S products retire)
+//                 of the head as [SP x 64] SWIZZLE_128B boxes of the packed qkv tensor; the additive key-mask row in
+//                 the exp2 domain and (kc, nfast): when the mask row is a prefix of ones -- every UC2 collate makes
+//                 such rows -- only the first kc = ceil16(valid keys) columns are computed at all (a masked key's
+//                 probability exp(s - 10000 - max) is exactly 0 in fp32 next to any valid key) and the chunks that
+//                 hold valid keys only skip the bias arithmetic; any other 0/1 row takes the general path
+//     warp 1      one thread issues  S_t = Q_t K^T  (M 128, N kc, K 64) into TMEM and, once the softmax warps have
+//                 published P_t,  O_t = P_t V  with A = P_t read from TENSOR MEMORY (K-major) and B = V, MN-major,
+//                 straight from its [key][d] rows
+//     warps 2-9   a thread owns ONE query row (TMEM lane) and, with FWD_NSPLIT warps per lane quarter, a column range
+//                 of it: row max / row sum are exchanged through shared memory between the parts, two passes over
+//                 the scores in TMEM (max; exp2 + sum + the counter-hash dropout of attention.cu), P stored as bf16
+//                 pairs back into tensor memory; then the epilogue O / rowsum -> ctx, lse.
+template <bool DROP>
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_q0,
+                        const __grid_constant__ CUtensorMap tmap_q1, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
     const int S = p.S, SP = p.SP;
     const TcSmem L = tc_smem(S, SP);
     float* mbias = reinterpret_cast<float*>(gen + L.off_mbias);
+    volatile int* info = reinterpret_cast<volatile int*>(gen + L.off_info);     // [buf][kc, nfast]
+    float* red_max = reinterpret_cast<float*>(gen + L.off_red);
+    float* red_sum = red_max + FWD_EW * 32;
     const uint32_t bar = base + L.off_bar;
-    // barriers (8 B each): full[2] empty[2] s_full[2] p_full[2] o_full[2] o_empty[2], then the TMEM base address
-    auto full_bar = [&](int b) { return bar + 8u * b; };
-    auto empty_bar = [&](int b) { return bar + 16u + 8u * b; };
-    auto sfull_bar = [&](int t) { return bar + 32u + 8u * t; };
-    auto pfull_bar = [&](int t) { return bar + 48u + 8u * t; };
-    auto ofull_bar = [&](int t) { return bar + 64u + 8u * t; };
-    auto oempty_bar = [&](int t) { return bar + 80u + 8u * t; };
+    // barriers (8 B each): kv_full[2] kv_empty[2] q_full[2] q_empty[2] (per query tile) s_full p_full o_full o_empty,
+    // then the TMEM base address
+    auto kvfull_bar = [&](int b) { return bar + 8u * b; };
+    auto kvempty_bar = [&](int b) { return bar + 16u + 8u * b; };
+    auto qfull_bar = [&](int t) { return bar + 32u + 8u * t; };
+    auto qempty_bar = [&](int t) { return bar + 48u + 8u * t; };
+    const uint32_t sfull_bar = bar + 64u, pfull_bar = bar + 72u, ofull_bar = bar + 80u, oempty_bar = bar + 88u;
     const uint32_t tmem_ptr_addr = bar + 96u;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen + L.off_bar + 96);
 
@@ -146,22 +277,25 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const TcPa
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmap_qkv);
+        ptx::prefetch_tmap(&tmap_q0);
+        ptx::prefetch_tmap(&tmap_q1);
         for (int b = 0; b < 2; ++b) {
-            ptx::mbar_init(full_bar(b), 2);            // TMA transaction arrive + mask-row arrive
-            ptx::mbar_init(empty_bar(b), 1);
+            ptx::mbar_init(kvfull_bar(b), 2);          // TMA transaction arrive + mask-row arrive
+            ptx::mbar_init(kvempty_bar(b), 1);
         }
         for (int t = 0; t < 2; ++t) {
-            const int na = active_warps(S, t);
-            ptx::mbar_init(sfull_bar(t), 1);
-            ptx::mbar_init(pfull_bar(t), na > 0 ? na : 1);
-            ptx::mbar_init(ofull_bar(t), 1);
-            ptx::mbar_init(oempty_bar(t), na > 0 ? na : 1);
+            ptx::mbar_init(qfull_bar(t), 1);
+            ptx::mbar_init(qempty_bar(t), 1);
         }
+        ptx::mbar_init(sfull_bar, 1);
+        ptx::mbar_init(pfull_bar, FWD_EW);             // every softmax warp arrives, also those without rows
+        ptx::mbar_init(ofull_bar, 1);
+        ptx::mbar_init(oempty_bar, FWD_EW);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_ptr_addr, TMEM_COLS);
+        ptx::tmem_alloc(tmem_ptr_addr, L.tm_cols);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -172,145 +306,201 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const TcPa
 
     if (warp == 0) {
         // ===================================== producer =====================================
+        PhaseClock pc(p.prof, FWD_THREADS / 32);
         int it = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t ph = (it >> 1) & 1u;
             const int b = item / NH, h = item - b * NH;
-            if (lane == 0) ptx::mbar_wait(empty_bar(buf), ph ^ 1u);   // the MMAs of item it - 2 retired
+            pc.lap(0);
+            if (lane == 0) ptx::mbar_wait(kvempty_bar(buf), ph ^ 1u);   // the P V products of item it - 2 retired
             __syncwarp();
+            pc.lap(1);
             if (lane == 0) {
-                const uint32_t dst = base + buf * L.buf_bytes;
-                ptx::mbar_arrive_expect_tx(full_bar(buf), L.buf_bytes);
-                ptx::tma_load_2d(dst, &tmap_qkv, full_bar(buf), h * HD, b * S);
-                ptx::tma_load_2d(dst + L.tile_bytes, &tmap_qkv, full_bar(buf), HID + h * HD, b * S);
-                ptx::tma_load_2d(dst + 2u * L.tile_bytes, &tmap_qkv, full_bar(buf), 2 * HID + h * HD, b * S);
+                const uint32_t dst = base + L.off_kv + buf * 2u * L.tile_bytes;
+                ptx::mbar_arrive_expect_tx(kvfull_bar(buf), 2u * L.tile_bytes);
+                ptx::tma_load_2d(dst, &tmap_qkv, kvfull_bar(buf), HID + h * HD, b * S);
+                ptx::tma_load_2d(dst + L.tile_bytes, &tmap_qkv, kvfull_bar(buf), 2 * HID + h * HD, b * S);
             }
             // additive key mask of model.py:433-436 in the exp2 domain; padding columns [S, SP) never contribute
             float* mb = mbias + buf * SP;
             const long long* mrow = p.mask + (long long)b * S;
-            for (int j = lane; j < SP; j += 32) mb[j] = j < S ? (mrow[j] != 0 ? 0.f : MASK_LOG2) : -INFINITY;
+            int ones = 0, last = -1;
+            for (int j = lane; j < SP; j += 32) {
+                const bool on = j < S && mrow[j] != 0;
+                mb[j] = j < S ? (on ? 0.f : MASK_LOG2) : -INFINITY;
+                if (on) { ++ones; last = j; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ones += __shfl_xor_sync(0xffffffffu, ones, o);
+                last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+            }
+            if (lane == 0) {
+                const bool prefix = ones > 0 && last + 1 == ones;
+                info[2 * buf] = prefix ? (ones + 15) & ~15 : SP;      // kc: score columns computed
+                info[2 * buf + 1] = prefix ? ones & ~15 : 0;          // nfast: leading columns without bias arithmetic
+            }
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(full_bar(buf));
+            pc.lap(2);
+            if (lane == 0) {
+                ptx::mbar_arrive(kvfull_bar(buf));
+                // a query tile's buffer is free once the previous item's S product of that tile retired
+                ptx::mbar_wait(qempty_bar(0), (it & 1u) ^ 1u);
+                ptx::mbar_arrive_expect_tx(qfull_bar(0), (SP < 128 ? SP : 128) * 128u);
+                ptx::tma_load_2d(base, &tmap_q0, qfull_bar(0), h * HD, b * S);
+                if (L.nt == 2) {
+                    ptx::mbar_wait(qempty_bar(1), (it & 1u) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(qfull_bar(1), L.rem * 128u);
+                    ptx::tma_load_2d(base + L.off_q1, &tmap_q1, qfull_bar(1), h * HD, b * S + 128);
+                }
+            }
+            __syncwarp();
+            pc.lap(3);
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer ===================================
+        // Issue order: S(0); then per unit n: [P_n published] O_n = P_n V, and straight behind it S(n+1) -- the tensor
+        // pipe runs in issue order, so S(n+1) overwrites the S / P columns only after O_n has read P_n, and it is
+        // ready by the time the softmax warps are through with the epilogue of unit n.
         if (lane == 0) {
-            const uint32_t idesc_s = ptx::idesc_bf16_f32(128, SP, false, false);
             const uint32_t idesc_o = ptx::idesc_bf16_f32(128, HD, false, true);
-            int it = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const uint32_t ph = (it >> 1) & 1u, itp = it & 1u;
-                ptx::mbar_wait(full_bar(buf), ph);
+            const int my_items = p.items > (int)blockIdx.x ? (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            const uint32_t units = static_cast<uint32_t>(my_items) * L.nt;
+            PhaseClock pc(p.prof, FWD_THREADS / 32);
+            auto issue_s = [&](uint32_t n) {
+                const int it = n / L.nt, t = n - it * L.nt, buf = it & 1;
+                pc.lap(0);
+                if (t == 0) ptx::mbar_wait(kvfull_bar(buf), (it >> 1) & 1u);
+                ptx::mbar_wait(qfull_bar(t), it & 1u);
+                pc.lap(1);
                 ptx::tc_fence_after();
-                const uint32_t sQ = base + buf * L.buf_bytes, sK = sQ + L.tile_bytes, sV = sK + L.tile_bytes;
-                // S_t = Q_t K^T.  The S columns are free: p_full(t) of the previous item was waited on below.
-                // Tile 1 reads 128 rows from Q row 128 on; rows past SP are the K tile (finite, never stored).
-                for (int t = 0; t < L.nt; ++t) {
+                const int kc = info[2 * buf];
+                const uint32_t idesc_s = ptx::idesc_bf16_f32(128, kc, false, false);
+                const uint32_t sK = base + L.off_kv + buf * 2u * L.tile_bytes;
+                const uint32_t rot = L.rot_step * ((it + blockIdx.x) % L.rot_n);
+                // Tile 1: the valid rows sit at M rows rot.. of a 128-row window over whatever surrounds them in
+                // shared memory (those results are never read).
+                const uint32_t sQ = t == 0 ? base : base + L.off_q1 - rot * 128u;
+                // one descriptor per operand, advanced by 32 bytes (2 in the 16-byte address field) per 16 of head dim
+                const uint64_t da = ptx::smem_desc_sw128(sQ, 16u, 1024u), db = ptx::smem_desc_sw128(sK, 16u, 1024u);
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) {
-                        const uint64_t da = ptx::smem_desc_sw128(sQ + t * 16384u + k * 32u, 16u, 1024u);
-                        const uint64_t db = ptx::smem_desc_sw128(sK + k * 32u, 16u, 1024u);
-                        ptx::umma_bf16(tmem_base + TM_S + t * TM_S_STRIDE, da, db, idesc_s, k > 0 ? 1u : 0u);
-                    }
-                    ptx::umma_commit(sfull_bar(t));
+                for (int k = 0; k < HD / 16; ++k) ptx::umma_bf16(tmem_base, da + 2u * k, db + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                ptx::umma_commit(sfull_bar);
+                ptx::umma_commit(qempty_bar(t));           // this query tile is dead once the product retires
+                pc.lap(2);
+            };
+            if (units > 0) issue_s(0);
+            for (uint32_t n = 0; n < units; ++n) {
+                const int it = n / L.nt, t = n - it * L.nt, buf = it & 1;
+                const int kc = info[2 * buf];
+                const int nch = kc >> 4, per = (nch + FWD_NSPLIT - 1) / FWD_NSPLIT;
+                const uint32_t sV = base + L.off_kv + buf * 2u * L.tile_bytes + L.tile_bytes;
+                pc.lap(0);
+                ptx::mbar_wait(pfull_bar, n & 1u);
+                pc.lap(3);
+                if (n > 0) ptx::mbar_wait(oempty_bar, (n - 1u) & 1u);      // the previous unit's O has been read out
+                pc.lap(4);
+                ptx::tc_fence_after();
+                // O = P V: A = the bf16 P tile in tensor memory (8 columns per 16 keys, each softmax part's share at the
+                // start of its own column range), B = V rows, MN-major
+                uint64_t dv = ptx::smem_desc_sw128(sV, 8192u, 1024u);      // + 2048 bytes (128) per 16 keys
+                uint32_t acc = 0u;
+                for (int part = 0; part < FWD_NSPLIT; ++part) {
+                    uint32_t a = tmem_base + part * per * 16;
+                    const int cnt = min(per, nch - part * per);
+                    for (int i = 0; i < cnt; ++i, a += 8u, dv += 128u, acc = 1u)
+                        ptx::umma_bf16_ts(tmem_base + L.tm_o, a, dv, idesc_o, acc);
                 }
-                // O_t = P_t V once group t has written P_t and read the previous item's O_t
-                for (int t = 0; t < L.nt; ++t) {
-                    ptx::mbar_wait(pfull_bar(t), itp);
-                    ptx::mbar_wait(oempty_bar(t), itp ^ 1u);
-                    ptx::tc_fence_after();
-                    const uint32_t sP = base + L.off_p + t * L.p_tile_bytes;
-                    for (int kk = 0; kk < SP / 16; ++kk) {
-                        const uint64_t da =
-                            ptx::smem_desc_sw128(sP + (kk >> 2) * P_CHUNK_BYTES + (kk & 3) * 32u, 16u, 1024u);
-                        const uint64_t db = ptx::smem_desc_sw128(sV + kk * 2048u, 8192u, 1024u);
-                        ptx::umma_bf16(tmem_base + TM_O + t * TM_O_STRIDE, da, db, idesc_o, kk > 0 ? 1u : 0u);
-                    }
-                    ptx::umma_commit(ofull_bar(t));
-                }
-                ptx::umma_commit(empty_bar(buf));       // Q, K, V of this buffer are dead once all of the above retire
+                ptx::umma_commit(ofull_bar);
+                if (t == L.nt - 1) ptx::umma_commit(kvempty_bar(buf));     // K, V of this buffer are dead once these retire
+                pc.lap(5);
+                if (n + 1 < units) issue_s(n + 1);
             }
         }
     } else {
-        // ===================================== softmax groups ================================
-        const int t = (warp - 2) >> 2;              // query tile of this group
+        // ===================================== softmax warps ================================
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
-        if (t * 128 + q * 32 < S) {
-            const int row = t * 128 + q * 32 + lane;                  // query row inside the (batch, head)
-            const bool row_ok = row < S;
-            const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-            const uint32_t tS = tmem_base + lane_sel + TM_S + t * TM_S_STRIDE;
-            const uint32_t tO = tmem_base + lane_sel + TM_O + t * TM_O_STRIDE;
-            const uint32_t prow = base + L.off_p + t * L.p_tile_bytes + static_cast<uint32_t>(q * 32 + lane) * 128u;
-            const uint32_t sw = static_cast<uint32_t>(lane & 7);
-            const uint32_t row_idx0 = static_cast<uint32_t>(row) * static_cast<uint32_t>(S);
-            int it = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const uint32_t ph = (it >> 1) & 1u, itp = it & 1u;
-                const int b = item / NH, h = item - b * NH;
-                const float* mb = mbias + buf * SP;
-                const uint32_t hkey = drop_head_key(p.drop.key, b * NH + h);
-                ptx::mbar_wait(full_bar(buf), ph);                    // the mask row is there
-                ptx::mbar_wait(sfull_bar(t), itp);                    // ... and so is S_t (and P_t is free again)
-                ptx::tc_fence_after();
+        const int part = (warp - 2) >> 2;           // which column range of the row
+        const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t tS = tmem_base + lane_sel;
+        const uint32_t tO = tmem_base + lane_sel + L.tm_o + part * (HD / FWD_NSPLIT);
+        const int slot = (part * 4 + q) * 32 + lane;
+        const float out_scale = DROP ? p.drop.scale : 1.f;
+        // epilogue of a unit: O / rowsum -> ctx (heads merged: layer.py:98-100 is free), lse for the backward.  It is
+        // deferred until the NEXT unit's scores have arrived: S(n+1) is issued behind O_n = P_n V and the tensor pipe
+        // runs in order, so s_full(n+1) also says O_n is complete -- one barrier round trip per unit instead of two.
+        struct Pending { bf16* orow; float* lse; float m, l; bool active, row_ok; } prev = {nullptr, nullptr, 0.f, 1.f, false, false};
+        auto epilogue = [&](const Pending& e) {
+            if (e.active) {
                 uint32_t r[32];
-                float m = -INFINITY;
-                int c = 0;
-                for (; c + 32 <= SP; c += 32) {
-                    ptx::tmem_ld_32x32(tS + c, r);
-                    ptx::tmem_wait_ld();
-                    m = max_chunk<32>(r, mb, c, m);
-                }
-                if (c < SP) {
-                    ptx::tmem_ld_32x16(tS + c, r);
-                    ptx::tmem_wait_ld();
-                    m = max_chunk<16>(r, mb, c, m);
-                }
-                float l = 0.f;
-                for (c = 0; c + 32 <= SP; c += 32) {
-                    ptx::tmem_ld_32x32(tS + c, r);
-                    ptx::tmem_wait_ld();
-                    softmax_chunk<32>(r, mb, c, m, l, p.drop, hkey, row_idx0, prow, sw);
-                }
-                if (c < SP) {
-                    ptx::tmem_ld_32x16(tS + c, r);
-                    ptx::tmem_wait_ld();
-                    softmax_chunk<16>(r, mb, c, m, l, p.drop, hkey, row_idx0, prow, sw);
-                }
-                ptx::fence_proxy_async();        // P_t: generic-proxy stores -> visible to the tensor core's reads
-                ptx::tc_fence_before();          // S_t reads are complete (wait::ld above) before the barrier
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(pfull_bar(t));
-
-                // epilogue: O_t / rowsum -> ctx (heads merged: layer.py:98-100 is free), lse for the backward
-                ptx::mbar_wait(ofull_bar(t), itp);
-                ptx::tc_fence_after();
-                const float inv = 1.f / l;
-                bf16* orow = p.ctx + ((long long)b * S + row) * HID + h * HD;
+                constexpr int W = HD / FWD_NSPLIT;
+                static_assert(W == 32, "the epilogue reads one 32-column block per part");
+                ptx::tmem_ld_32x32(tO, r);
+                ptx::tmem_wait_ld();
+                if (e.row_ok) {
+                    const float inv = out_scale / e.l;
 #pragma unroll
-                for (int c2 = 0; c2 < HD; c2 += 32) {
-                    ptx::tmem_ld_32x32(tO + c2, r);
-                    ptx::tmem_wait_ld();
-                    if (row_ok) {
+                    for (int g = 0; g < 2; ++g) {
+                        uint32_t o[8];
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            uint32_t o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                o[j] = pack_bf16(__uint_as_float(r[16 * g + 2 * j]) * inv,
-                                                 __uint_as_float(r[16 * g + 2 * j + 1]) * inv);
-                            ptx::stg256(orow + c2 + 16 * g, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
-                        }
+                        for (int j = 0; j < 8; ++j)
+                            o[j] = pack_bf16(__uint_as_float(r[16 * g + 2 * j]) * inv,
+                                             __uint_as_float(r[16 * g + 2 * j + 1]) * inv);
+                        ptx::stg256(e.orow + 16 * g, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
                     }
+                    if (part == 0) *e.lse = (e.m + log2f(e.l)) * (1.f / LOG2E);
                 }
-                if (row_ok) p.lse[((long long)b * NH + h) * S + row] = (m + log2f(l)) * (1.f / LOG2E);
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(oempty_bar(t));
             }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(oempty_bar);
+        };
+        PhaseClock pc(p.prof, FWD_THREADS / 32);
+        int it = 0;
+        uint32_t n = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int b = item / NH, h = item - b * NH;
+            const float* mb = mbias + buf * SP;
+            const uint32_t hkey = drop_head_key(p.drop.key, b * NH + h);
+            pc.lap(0);
+            ptx::mbar_wait(kvfull_bar(buf), (it >> 1) & 1u);          // the mask row and (kc, nfast) are there
+            pc.lap(1);
+            const int kc = info[2 * buf], nfast = info[2 * buf + 1];
+            const int nch = kc >> 4, per = (nch + FWD_NSPLIT - 1) / FWD_NSPLIT;
+            const int c_begin = min(part * per, nch) * 16, c_end = min((part + 1) * per, nch) * 16;
+            const int rot = L.rot_step * ((it + blockIdx.x) % L.rot_n);
+            for (int t = 0; t < L.nt; ++t, ++n) {
+                // tile 0: lanes = rows 0..127; tile 1: lanes rot.. = rows 128.. (see tc_smem)
+                const int rel = q * 32 + lane - (t ? rot : 0);
+                const int row = t * 128 + rel;                        // query row inside the (batch, head)
+                Pending cur;
+                cur.row_ok = rel >= 0 && row < S;
+                cur.active = __any_sync(0xffffffffu, cur.row_ok);     // uniform over the warps of a lane quarter
+                cur.orow = p.ctx + ((long long)b * S + row) * HID + h * HD + part * (HD / FWD_NSPLIT);
+                cur.lse = p.lse + ((long long)b * NH + h) * S + row;
+                cur.m = 0.f; cur.l = 1.f;
+                pc.lap(0);
+                ptx::mbar_wait(sfull_bar, n & 1u);
+                pc.lap(2);
+                ptx::tc_fence_after();
+                if (n > 0) epilogue(prev);
+                pc.lap(3);
+                if (cur.active)
+                    softmax_row<DROP>(tS, mb, c_begin, c_end, nfast, red_max, red_sum, slot, q, lane,
+                                      p.drop.thresh << 16, hkey, static_cast<uint32_t>(cur.row_ok ? row : 0), cur.m, cur.l);
+                ptx::tc_fence_before();          // S_t reads and P_t stores are complete before the barrier
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(pfull_bar);
+                pc.lap(cur.active ? 4 : 5);
+                prev = cur;
+            }
+        }
+        if (n > 0) {
+            ptx::mbar_wait(ofull_bar, (n - 1u) & 1u);
+            ptx::tc_fence_after();
+            epilogue(prev);
         }
     }
 
@@ -319,7 +509,7 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const TcPa
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        ptx::tmem_dealloc(tmem_base, L.tm_cols);
     }
 }
 
@@ -363,6 +553,8 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int S, int SP) {
     return L;
 }
 
+constexpr int TC_BWD_MAX_SP = 160;
+constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMB_S = 0, TMB_DP = 192, TMB_DV = 0, TMB_DK = 64, TMB_DQ = 384;
 
 // W (16, 32 or 64) accumulator columns of this thread's row, times `scale`, -> W bf16 at dst
@@ -675,14 +867,18 @@ extern "C" UC2_API int uc2_attention_fwd_tc(const void* qkv, const long long* at
                 "attention_fwd_tc: qkv must be 16-byte and ctx 32-byte aligned");
     // qkv as a 2-D bf16 tensor [B*S][2304]; one box = the SP x 64 tile of one head's Q, K or V (rows past B*S are
     // zero-filled, rows past S inside the box belong to the next sample and are masked / never stored)
-    CUtensorMap tmap;
-    if (int rc = make_tmap(&tmap, qkv, (long long)B * S, QKV_LD, QKV_LD, SP)) return rc;
     const TcSmem L = tc_smem(S, SP);
+    CUtensorMap tmap, tq0, tq1;
+    if (int rc = make_tmap(&tmap, qkv, (long long)B * S, QKV_LD, QKV_LD, SP)) return rc;
+    if (int rc = make_tmap(&tq0, qkv, (long long)B * S, QKV_LD, QKV_LD, SP < 128 ? SP : 128)) return rc;
+    if (int rc = make_tmap(&tq1, qkv, (long long)B * S, QKV_LD, QKV_LD, L.rem > 0 ? L.rem : 16)) return rc;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(tc_smem(TC_MAX_SP, TC_MAX_SP).total));
+        const int bytes = static_cast<int>(tc_smem(TC_MAX_SP, TC_MAX_SP).total);
+        attr_err = cudaFuncSetAttribute(attention_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(attention_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     });
     UC2_REQUIRE(attr_err == cudaSuccess, UC2_ERR_CUDA, "attention_fwd_tc: cudaFuncSetAttribute failed: %s",
                 cudaGetErrorString(attr_err));
@@ -692,11 +888,41 @@ extern "C" UC2_API int uc2_attention_fwd_tc(const void* qkv, const long long* at
     p.lse = lse;
     p.B = B; p.S = S; p.SP = SP; p.items = B * NH;
     p.drop = DropCfg{drop_key, drop_thresh, drop_scale};
-    const int grid = p.items < num_sms() ? p.items : num_sms();
+    p.prof = nullptr;
+    static const bool prof_on = [] { const char* e = getenv("UC2_ATTN_PROF"); return e && e[0] == '1'; }();
+    static long long* prof_buf = nullptr;
+    const int prof_words = 2 * 148 * (FWD_THREADS / 32) * PROF_SLOTS;
+    if (prof_on) {
+        if (!prof_buf) cudaMalloc(&prof_buf, prof_words * sizeof(long long));
+        cudaMemsetAsync(prof_buf, 0, prof_words * sizeof(long long), (cudaStream_t)stream);
+        p.prof = prof_buf;
+    }
+    // SP <= 160: two CTAs per SM (256 TMEM columns and < 113 KB of shared memory each); above: one, with all 512
+    const bool pair = L.tm_cols == 256u;
+    const int slots = (pair ? 2 : 1) * num_sms();
+    const int grid = p.items < slots ? p.items : slots;
     ProfScope prof((cudaStream_t)stream, 1, 4.0 * B * NH * (double)S * S * HD);
-    const cudaError_t e = launch_pdl(attention_fwd_tc_kernel, dim3(grid), dim3(TC_THREADS), exclusive_smem(L.total),
-                                     (cudaStream_t)stream, 1, tmap, p);
+    const size_t smem = pair ? L.total : exclusive_smem(L.total);
+    const cudaError_t e = drop_thresh ? launch_pdl(attention_fwd_tc_kernel<true>, dim3(grid), dim3(FWD_THREADS), smem,
+                                                   (cudaStream_t)stream, 1, tmap, tq0, tq1, p)
+                                      : launch_pdl(attention_fwd_tc_kernel<false>, dim3(grid), dim3(FWD_THREADS), smem,
+                                                   (cudaStream_t)stream, 1, tmap, tq0, tq1, p);
     UC2_REQUIRE(e == cudaSuccess, UC2_ERR_CUDA, "attention_fwd_tc launch failed: %s", cudaGetErrorString(e));
+    if (prof_on) {        // debug only: synchronises; prints the phase cycle counters of CTA 0 and of the last CTA
+        static int printed = 0;
+        cudaStreamSynchronize((cudaStream_t)stream);
+        if (printed++ < 4) {
+            const int W = FWD_THREADS / 32;
+            static long long host[2 * 148 * (FWD_THREADS / 32) * PROF_SLOTS];
+            cudaMemcpy(host, prof_buf, prof_words * sizeof(long long), cudaMemcpyDeviceToHost);
+            for (int c : {0, grid / 2, grid - 1})
+                for (int w = 0; w < W; ++w) {
+                    fprintf(stderr, "attn_fwd_tc prof B=%d S=%d drop=%u cta %d warp %d:", B, S, drop_thresh, c, w);
+                    for (int k = 0; k < PROF_SLOTS; ++k) fprintf(stderr, " %lld", host[((long long)c * W + w) * PROF_SLOTS + k]);
+                    fprintf(stderr, "\n");
+                }
+        }
+    }
     return check_last("attention_fwd_tc_kernel");
 }
 
@@ -709,7 +935,7 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     UC2_REQUIRE(B > 0 && S > 0, UC2_ERR_ARG, "attention_bwd_tc: bad shape B=%d S=%d", B, S);
     UC2_REQUIRE(drop_thresh < 65536u, UC2_ERR_ARG, "attention_bwd_tc: drop_thresh must be < 65536");
     const int SP = (S + 15) / 16 * 16;
-    UC2_REQUIRE(SP <= TC_MAX_SP, UC2_ERR_UNSUPPORTED, "attention_bwd_tc: S=%d > %d", S, TC_MAX_SP);
+    UC2_REQUIRE(SP <= TC_BWD_MAX_SP, UC2_ERR_UNSUPPORTED, "attention_bwd_tc: S=%d > %d", S, TC_BWD_MAX_SP);
     UC2_REQUIRE(aligned16(qkv) && aligned16(ctx) && aligned16(dctx) && (reinterpret_cast<uintptr_t>(dqkv) & 31) == 0,
                 UC2_ERR_ARG, "attention_bwd_tc: qkv / ctx / dctx must be 16-byte and dqkv 32-byte aligned");
     CUtensorMap tq, tdo;
@@ -722,7 +948,7 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     std::call_once(once, [] {
         const char* e = getenv("UC2_ATTN_TC_BWD_SPLIT");          // tuning knob: 2 (default) or 4 warps per lane quarter
         if (e && e[0] == '4') nsplit = 4;
-        const int bytes = static_cast<int>(tc_bwd_smem(TC_MAX_SP, TC_MAX_SP).total);
+        const int bytes = static_cast<int>(tc_bwd_smem(TC_BWD_MAX_SP, TC_BWD_MAX_SP).total);
         attr_err = cudaFuncSetAttribute(attention_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attention_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

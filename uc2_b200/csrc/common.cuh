@@ -176,6 +176,32 @@ __host__ __device__ __forceinline__ uint32_t drop_head_key(uint32_t key, uint32_
     return lowbias32(key ^ (bh * 0x9E3779B9u + 0x7F4A7C15u));
 }
 
+// Attention-probability dropout (layer.py:94) of the tcgen05 kernels.  The forward walks a query ROW (thread = query,
+// loop over keys), the backward a key ROW (thread = key, loop over queries); a per-element mix would cost more than the
+// softmax arithmetic itself in both.  So the [S x S] mask of a (batch, head) is tiled in 16 x 16 blocks: one lowbias32
+// per block, then element (i, j) takes  e = h_block * CA^(i & 15) * CB^(j & 15)  (mod 2^32; CA, CB odd, so every
+// element's e is a bijection of the block hash and exactly uniform) and is kept iff e >= thresh << 16.  Whichever
+// index a thread owns contributes a per-thread factor, the other one compile-time immediates: one IMAD + one ISETP
+// per element in either orientation.  Host mirror: uc2_b200/dropout.py attn_keep_mask_np.
+constexpr uint32_t DROP_CA = 0x9E3779B1u, DROP_CB = 0x85EBCA77u;
+__host__ __device__ constexpr uint32_t drop_pow(uint32_t c, int k) {
+    uint32_t r = 1u;
+    for (int i = 0; i < k; ++i) r *= c;
+    return r;
+}
+// c^(k & 15) for a run-time k
+__device__ __forceinline__ uint32_t drop_pow_rt(uint32_t c, uint32_t k) {
+    const uint32_t c2 = c * c, c4 = c2 * c2, c8 = c4 * c4;
+    uint32_t r = (k & 1u) ? c : 1u;
+    r *= (k & 2u) ? c2 : 1u;
+    r *= (k & 4u) ? c4 : 1u;
+    r *= (k & 8u) ? c8 : 1u;
+    return r;
+}
+__device__ __forceinline__ uint32_t drop_block_hash(uint32_t hkey, uint32_t iblk, uint32_t jblk) {
+    return lowbias32(hkey ^ ((iblk << 16) | jblk));
+}
+
 // erf-form GELU (model/layer.py:31-37) and its derivative.
 // 0.5 erfc(|x|/sqrt2) through Abramowitz-Stegun 7.1.25: erfc(z) = t (a1 + t (a2 + t a3)) exp(-z^2),
 // t = 1 / (1 + p z), z >= 0, |error| <= 2.5e-5 on erf.  The results are rounded to bf16 (half an ulp is 2e-3

@@ -237,6 +237,16 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// wait::ld that also names the 16 destination registers of an in-flight load as read-write operands, so the compiler
+// cannot schedule a use of them above the wait (software-pipelined loads: the registers are "written" at the wait)
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
 // 32 lanes x 32 columns of fp32: thread i of the warp receives row (lane base + i), 32 consecutive columns.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -262,7 +272,14 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 
-// ---- not used by a kernel yet: the primitives the tcgen05 attention port needs ----
+// L2 prefetch of a 2-D box (no shared-memory destination, no completion mechanism): warms the next work item's tiles
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// ---- register -> tensor memory stores and the TMEM-A MMA form (attention: P never visits shared memory) ----
 // Store 32 lanes x 16 columns (32-bit each) from registers to tensor memory: thread i writes row (lane base + i).
 // Two bf16 packed per column make a K-major A operand of 32 k-values per row for umma_bf16_ts().
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
@@ -272,6 +289,11 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r)
         "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[TENSOR MEMORY, K-major only] * B[smem desc]: the P V product of attention without a trip of P through

@@ -66,6 +66,23 @@ def lowbias32_np(x):
     return x
 
 
+ATTN_CA, ATTN_CB = 0x9E3779B1, 0x85EBCA77
+
+
+def attn_keep_mask_np(hkey, S, thresh):
+    """[S, S] boolean keep mask (query, key) of one (batch, head) for the tcgen05 attention kernels
+    (csrc/common.cuh, "Attention-probability dropout"): one lowbias32 per 16 x 16 block, element (i, j) takes
+    e = h_block * CA^(i & 15) * CB^(j & 15) mod 2^32 and is kept iff e >= thresh << 16."""
+    i = np.arange(S, dtype=np.uint32)
+    blk = ((i[:, None] >> np.uint32(4)) << np.uint32(16)) | (i[None, :] >> np.uint32(4))
+    h = lowbias32_np(blk ^ np.uint32(hkey)).astype(np.uint64)
+    pa = np.array([pow(ATTN_CA, k, 1 << 32) for k in range(16)], dtype=np.uint64)
+    pb = np.array([pow(ATTN_CB, k, 1 << 32) for k in range(16)], dtype=np.uint64)
+    m = np.uint64(M32)
+    e = (((h * pa[i & np.uint32(15)][:, None]) & m) * pb[i & np.uint32(15)][None, :]) & m
+    return e >= np.uint64(int(thresh) << 16)
+
+
 def keep_mask_np(key, n, thresh, idx=None):
     """Boolean keep mask of elements 0..n-1 (or of the given uint32 index array) under `key`."""
     if idx is None:
