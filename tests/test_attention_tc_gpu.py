@@ -127,10 +127,13 @@ def test_tc_rejects_long_sequences():
     assert rc != 0
 
 
-def _ref_bwd(qkv, mask, dctx, B, S):
+def _ref_bwd(qkv, mask, dctx, B, S, keep=None, scale=1.0):
     x = qkv.float().view(B, S, 3, 12, 64).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
     sc = x[0] @ x[1].transpose(-1, -2) / 8 + (1 - mask.float())[:, None, None, :] * -10000.0
-    o = (sc.softmax(-1) @ x[2]).permute(0, 2, 1, 3).reshape(B * S, 768)
+    pr = sc.softmax(-1)
+    if keep is not None:
+        pr = pr * keep * scale
+    o = (pr @ x[2]).permute(0, 2, 1, 3).reshape(B * S, 768)
     o.backward(dctx.float())
     return x.grad.permute(1, 3, 0, 2, 4).reshape(B * S, 2304)
 
@@ -170,17 +173,20 @@ def test_tc_backward_matches_reference_and_mma_sync(B, S, kind):
     assert (dqkv.float() - d0.float()).abs().max().item() <= 1.5e-2 * scale
 
 
-@pytest.mark.parametrize("B,S,kind", [(6, 160, "prefix"), (3, 77, "random"), (4, 150, "prefix")])
-def test_tc_backward_dropout_stream_is_the_mma_sync_one(B, S, kind):
+@pytest.mark.parametrize("B,S,kind", [(6, 160, "prefix"), (3, 77, "random"), (4, 150, "prefix"), (5, 33, "prefix")])
+def test_tc_backward_dropout_matches_reference_with_host_mirror_mask(B, S, kind):
+    """Forward and backward regenerate the same attention-dropout mask: torch autograd through the dropped
+    probabilities (mask from the host mirror) gives the gradients the kernel must produce."""
     qkv, mask = _inputs(B, S, kind)
     dctx = torch.randn(B * S, 768, device="cuda").bfloat16()
-    drop = (0x1234567, int(round(0.1 * 65536)), 1.0 / 0.9)
-    ctx, lse = _run("uc2_attention_fwd_dropout", qkv, mask, B, S, drop)
-    d_tc = _run_bwd("uc2_attention_bwd_tc", qkv, mask, ctx, dctx, lse, B, S, drop)
-    d0 = _run_bwd("uc2_attention_bwd_dropout", qkv, mask, ctx, dctx, lse, B, S, drop)
-    scale = d0.float().abs().max().item()
+    key, p = 0x7654321, 0.1
+    keep, t, scale = _keep_masks(key, B, S, p)
+    ctx, lse = _run("uc2_attention_fwd_tc", qkv, mask, B, S, (key, t, scale))
+    d_tc = _run_bwd("uc2_attention_bwd_tc", qkv, mask, ctx, dctx, lse, B, S, (key, t, scale))
+    g = _ref_bwd(qkv, mask, dctx, B, S, keep, scale)
+    sc = g.abs().max().item()
     assert torch.isfinite(d_tc.float()).all()
-    assert (d_tc.float() - d0.float()).abs().max().item() <= 1.5e-2 * scale
+    assert (d_tc.float() - g).abs().max().item() <= 1.5e-2 * sc
 
 
 @pytest.mark.parametrize("on", [0, 1])

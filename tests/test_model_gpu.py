@@ -13,18 +13,23 @@ import cases
 
 pytestmark = pytest.mark.gpu
 
-HID_TOL = 2e-2          # abs, north_star
-HID_RTOL = 2e-2         # bf16 stores 8 significant bits: half an ulp at |x| = 4 is already 1.6e-2
+HID_TOL = 2e-2          # abs, north_star: hidden states and logits within 2e-2 in bf16
+# bf16 stores 8 significant bits: half an ulp at |x| >= 4 is 1.6e-2, so after 12 layers a handful of the largest
+# elements land just outside 2e-2.  They are COUNTED and bounded instead of being hidden behind a relative term:
+HID_OUTLIER_FRAC = 2e-4  # at most this share of the elements may exceed HID_TOL ...
+HID_HARD = 5e-2          # ... and none may exceed this
 LOSS_RTOL = 1e-3
 np.set_printoptions(linewidth=250)
 
 
-def close(got, ref, atol=HID_TOL, rtol=HID_RTOL, what=""):
+def close(got, ref, atol=HID_TOL, what=""):
     got, ref = np.asarray(got, np.float32), np.asarray(ref, np.float32)
     d = np.abs(got - ref)
-    bad = d > atol + rtol * np.abs(ref)
-    assert not bad.any(), (f"{what}: {bad.sum()} of {bad.size} outside {atol}+{rtol}|ref|; max abs err "
-                           f"{d.max():.4f}, mean {d.mean():.5f}")
+    n_out = int((d > atol).sum())
+    print(f"{what}: {n_out} of {d.size} elements outside {atol} abs (allowed {int(HID_OUTLIER_FRAC * d.size)}), "
+          f"max abs err {d.max():.4f}, mean {d.mean():.5f}")
+    assert n_out <= HID_OUTLIER_FRAC * d.size and d.max() <= HID_HARD, (
+        f"{what}: {n_out} of {d.size} outside {atol} abs; max abs err {d.max():.4f}, mean {d.mean():.5f}")
     return d
 
 
@@ -295,7 +300,10 @@ def _dropout_multipliers(seed, counter, B, T, R, S, L, p_h, p_a):
     layers = []
     for l in range(L):
         ka = DO.site_key(seed, counter, l, DO.SITE_ATTN)
-        attn = torch.stack([f(DO.head_key(ka, bh), S * S, ta, sa).view(S, S) for bh in range(B * 12)]).view(B, 12, S, S)
+        # the tcgen05 attention kernels (the default for S <= 160) draw their mask from the 16 x 16 block stream
+        assert S <= 160
+        attn = torch.stack([torch.from_numpy(DO.attn_keep_mask_np(DO.head_key(ka, bh), S, ta).astype(np.float32) * np.float32(sa))
+                            for bh in range(B * 12)]).view(B, 12, S, S)
         o1 = f(DO.site_key(seed, counter, l, DO.SITE_OUT1), B * S * 768, th, sh).view(B, S, 768)
         o2 = f(DO.site_key(seed, counter, l, DO.SITE_OUT2), B * S * 768, th, sh).view(B, S, 768)
         layers.append((attn, o1, o2))

@@ -171,7 +171,8 @@ def call(name, *args):
 
 
 def attention_tc_enabled():
-    """Whether the public attention entry points currently route S <= 160 to the experimental tcgen05 kernels."""
+    """Whether the public attention entry points route to the tcgen05 kernels (the default; UC2_ATTN_TCGEN05=0 or
+    uc2_attention_tc_enable(0) switch back to the mma.sync kernels of csrc/attention.cu)."""
     prev = lib().uc2_attention_tc_enable(0)
     lib().uc2_attention_tc_enable(prev)
     return bool(prev)
@@ -179,7 +180,11 @@ def attention_tc_enabled():
 
 def attention_kernels(S):
     """Which attention kernels the public entry points run for a packed length S (for the bench line)."""
-    return "tcgen05/TMEM (attention_tc.cu)" if attention_tc_enabled() and S <= 160 else "mma.sync (attention.cu)"
+    if not attention_tc_enabled() or S > 256:
+        return "mma.sync (attention.cu)"
+    if S <= 160:
+        return "tcgen05/TMEM forward + backward (attention_tc.cu)"
+    return "tcgen05/TMEM forward when attention dropout is off, else mma.sync; mma.sync backward"
 
 
 def launch_count():

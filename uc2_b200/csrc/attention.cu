@@ -855,8 +855,12 @@ extern "C" UC2_API int uc2_attention_fwd_dropout(const void* qkv, const long lon
     UC2_REQUIRE(aligned16(qkv) && aligned16(ctx), UC2_ERR_ARG, "attention_fwd: qkv/ctx must be 16-byte aligned");
     int S_pad;
     if (int rc = attn_check(B, S, &S_pad)) return rc;
-    // opt-in tcgen05 / TMEM forward (attention_tc.cu), same results by construction; off unless enabled
-    if (attn_tc_enabled() && S <= 256 && (reinterpret_cast<uintptr_t>(ctx) & 31) == 0)
+    // tcgen05 / TMEM kernels (attention_tc.cu) unless switched off.  With attention dropout the forward and the backward
+    // have to regenerate the same mask, and the two kernel families draw it from different counter streams: the
+    // forward only goes there when the backward of this shape will too (attn_tc_bwd_serves).
+    // (The choice must not depend on pointer alignment, or the two passes could disagree: the tcgen05 entry points
+    // reject a ctx / dqkv that is not 32-byte aligned.)
+    if (attn_tc_enabled() && S <= 256 && (drop_thresh == 0 || attn_tc_bwd_serves(S)))
         return uc2_attention_fwd_tc(qkv, attn_mask, ctx, lse, B, S, drop_key, drop_thresh, drop_scale, stream);
     ProfScope prof((cudaStream_t)stream, 1, 4.0 * B * NH * (double)S * S * HD);
     if (S <= 256) {
@@ -893,7 +897,7 @@ extern "C" UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long lon
                 "attention_bwd: tensors must be 16-byte aligned");
     int S_pad;
     if (int rc = attn_check(B, S, &S_pad)) return rc;
-    if (attn_tc_enabled() && S <= 160 && (reinterpret_cast<uintptr_t>(dqkv) & 31) == 0)     // opt-in, see attention_tc.cu
+    if (attn_tc_enabled() && attn_tc_bwd_serves(S))
         return uc2_attention_bwd_tc(qkv, attn_mask, ctx, dctx, lse, dqkv, B, S, drop_key, drop_thresh, drop_scale, stream);
     cudaStream_t s = (cudaStream_t)stream;
     const long long rows = (long long)B * S;

@@ -313,6 +313,15 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             const uint32_t ph = (it >> 1) & 1u;
             const int b = item / NH, h = item - b * NH;
             pc.lap(0);
+            // the mask row first (global loads in flight under the wait below): additive key mask of model.py:433-436
+            // in the exp2 domain; padding columns [S, SP) never contribute
+            const long long* mrow = p.mask + (long long)b * S;
+            bool on[TC_MAX_SP / 32];
+#pragma unroll
+            for (int k = 0; k < TC_MAX_SP / 32; ++k) {
+                const int j = lane + 32 * k;
+                on[k] = j < S && mrow[j] != 0;
+            }
             if (lane == 0) ptx::mbar_wait(kvempty_bar(buf), ph ^ 1u);   // the P V products of item it - 2 retired
             __syncwarp();
             pc.lap(1);
@@ -322,14 +331,13 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 ptx::tma_load_2d(dst, &tmap_qkv, kvfull_bar(buf), HID + h * HD, b * S);
                 ptx::tma_load_2d(dst + L.tile_bytes, &tmap_qkv, kvfull_bar(buf), 2 * HID + h * HD, b * S);
             }
-            // additive key mask of model.py:433-436 in the exp2 domain; padding columns [S, SP) never contribute
             float* mb = mbias + buf * SP;
-            const long long* mrow = p.mask + (long long)b * S;
             int ones = 0, last = -1;
-            for (int j = lane; j < SP; j += 32) {
-                const bool on = j < S && mrow[j] != 0;
-                mb[j] = j < S ? (on ? 0.f : MASK_LOG2) : -INFINITY;
-                if (on) { ++ones; last = j; }
+#pragma unroll
+            for (int k = 0; k < TC_MAX_SP / 32; ++k) {
+                const int j = lane + 32 * k;
+                if (j < SP) mb[j] = j < S ? (on[k] ? 0.f : MASK_LOG2) : -INFINITY;
+                if (on[k]) { ++ones; last = j; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -533,6 +541,7 @@ struct TcBwdParams {
     bf16* dqkv;
     int B, S, SP, items;
     DropCfg drop;
+    long long* prof;      // debug (UC2_ATTN_PROF=1), see TcParams
 };
 
 struct TcBwdSmem {
@@ -545,7 +554,7 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int S, int SP) {
     L.nchunk = (SP + 63) >> 6;
     L.tile_bytes = SP * 128u;
     L.pt_bytes = L.nchunk * P_CHUNK_BYTES;
-    L.off_ds = 4u * L.tile_bytes;            // [Q][K][V][dO] then dS^T, then Pd^T (so MN-major over-reads of dS^T
+    L.off_ds = 5u * L.tile_bytes;            // [Q][K][V][dO][O] then dS^T, then Pd^T (so MN-major over-reads of dS^T
     L.off_pd = L.off_ds + L.pt_bytes;        // for the padding query blocks of dQ stay inside the allocation)
     L.off_vec = L.off_pd + L.pt_bytes;       // 2 buffers x (lse2[SP], delta[SP])
     L.off_bar = L.off_vec + 4u * SP * 4u;
@@ -582,7 +591,7 @@ __host__ __device__ constexpr int bwd_threads(int nsplit) { return 64 + 128 * ns
 template <int NSPLIT>
 __global__ void __launch_bounds__(bwd_threads(NSPLIT), 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                        const TcBwdParams p) {
+                        const __grid_constant__ CUtensorMap tmap_o, const TcBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
@@ -605,6 +614,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmap_qkv);
         ptx::prefetch_tmap(&tmap_do);
+        ptx::prefetch_tmap(&tmap_o);
         ptx::mbar_init(ld_full, 1);
         ptx::mbar_init(ld_empty, 1);
         for (int u = 0; u < 2; ++u) {
@@ -630,6 +640,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     griddep_sync();
 
     const uint32_t sQ = base, sK = sQ + L.tile_bytes, sV = sK + L.tile_bytes, sdO = sV + L.tile_bytes;
+    const uint8_t* gdO = gen + 3u * L.tile_bytes;        // generic-address views of the dO and O tiles (delta)
+    const uint8_t* gO = gen + 4u * L.tile_bytes;
     const uint32_t sDS = base + L.off_ds, sPD = base + L.off_pd;
 
     if (warp == 0) {
@@ -639,11 +651,21 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
                 const int b = item / NH, h = item - b * NH;
                 ptx::mbar_wait(ld_empty, (it & 1u) ^ 1u);          // every MMA of the previous item retired
-                ptx::mbar_arrive_expect_tx(ld_full, 4u * L.tile_bytes);
+                ptx::mbar_arrive_expect_tx(ld_full, 5u * L.tile_bytes);
                 ptx::tma_load_2d(sQ, &tmap_qkv, ld_full, h * HD, b * S);
                 ptx::tma_load_2d(sK, &tmap_qkv, ld_full, HID + h * HD, b * S);
                 ptx::tma_load_2d(sV, &tmap_qkv, ld_full, 2 * HID + h * HD, b * S);
                 ptx::tma_load_2d(sdO, &tmap_do, ld_full, h * HD, b * S);
+                ptx::tma_load_2d(sdO + L.tile_bytes, &tmap_o, ld_full, h * HD, b * S);
+                const int nxt = item + gridDim.x;                  // warm L2 with the next item's tiles
+                if (nxt < p.items) {
+                    const int nb = nxt / NH, nh = nxt - nb * NH;
+                    ptx::tma_prefetch_2d(&tmap_qkv, nh * HD, nb * S);
+                    ptx::tma_prefetch_2d(&tmap_qkv, HID + nh * HD, nb * S);
+                    ptx::tma_prefetch_2d(&tmap_qkv, 2 * HID + nh * HD, nb * S);
+                    ptx::tma_prefetch_2d(&tmap_do, nh * HD, nb * S);
+                    ptx::tma_prefetch_2d(&tmap_o, nh * HD, nb * S);
+                }
             }
         }
     } else if (warp == 1) {
@@ -652,50 +674,71 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             const uint32_t idesc_s = ptx::idesc_bf16_f32(128, SP, false, false);
             const uint32_t idesc_kv = ptx::idesc_bf16_f32(128, HD, false, true);
             const uint32_t idesc_dq = ptx::idesc_bf16_f32(128, HD, true, true);
+            PhaseClock pc(p.prof, bwd_threads(NSPLIT) / 32);
             int it = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
                 const uint32_t itp = it & 1u;
+                pc.lap(0);
                 ptx::mbar_wait(ld_full, itp);
+                pc.lap(1);
                 ptx::tc_fence_after();
                 for (int u = 0; u < nu; ++u) {
                     // TMEM [0,352) is free once the dV / dK of the previous key tile have been read out
+                    pc.lap(0);
                     if (u == 0) ptx::mbar_wait(s_empty(nu - 1), itp ^ 1u);
                     else ptx::mbar_wait(s_empty(u - 1), itp);
+                    pc.lap(2);
                     ptx::tc_fence_after();
                     // key tile 1 reads 128 rows from row 128 of K / V on; rows past SP are the following tiles
+                    // Consecutive products into the SAME accumulator run as a dependent chain (~80-90 cycles each
+                    // at these small N): products of independent accumulators are interleaved throughout.
+                    {
+                        const uint64_t dk = ptx::smem_desc_sw128(sK + u * 16384u, 16u, 1024u), dq = ptx::smem_desc_sw128(sQ, 16u, 1024u);
+                        const uint64_t dv = ptx::smem_desc_sw128(sV + u * 16384u, 16u, 1024u), dd = ptx::smem_desc_sw128(sdO, 16u, 1024u);
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        ptx::umma_bf16(tmem_base + TMB_S, ptx::smem_desc_sw128(sK + u * 16384u + k * 32u, 16u, 1024u),
-                                       ptx::smem_desc_sw128(sQ + k * 32u, 16u, 1024u), idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        ptx::umma_bf16(tmem_base + TMB_DP, ptx::smem_desc_sw128(sV + u * 16384u + k * 32u, 16u, 1024u),
-                                       ptx::smem_desc_sw128(sdO + k * 32u, 16u, 1024u), idesc_s, k > 0 ? 1u : 0u);
+                        for (int k = 0; k < HD / 16; ++k) {          // + 32 bytes (2 in the address field) per 16 of head dim
+                            ptx::umma_bf16(tmem_base + TMB_S, dk + 2u * k, dq + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                            ptx::umma_bf16(tmem_base + TMB_DP, dv + 2u * k, dd + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                        }
+                    }
                     ptx::umma_commit(sd_full(u));
+                    pc.lap(3);
 
                     ptx::mbar_wait(pds_full(u), itp);              // Pd^T_u, dS^T_u written; S^T, dP^T read
+                    pc.lap(4);
                     if (u == 0) ptx::mbar_wait(dq_empty, itp ^ 1u);   // previous item's dQ read out
+                    pc.lap(5);
                     ptx::tc_fence_after();
-                    for (int kk = 0; kk < SP / 16; ++kk) {         // K dimension = queries
-                        const uint32_t a_off = (kk >> 2) * P_CHUNK_BYTES + (kk & 3) * 32u;
-                        ptx::umma_bf16(tmem_base + TMB_DV, ptx::smem_desc_sw128(sPD + a_off, 16u, 1024u),
-                                       ptx::smem_desc_sw128(sdO + kk * 2048u, 8192u, 1024u), idesc_kv, kk > 0 ? 1u : 0u);
+                    // dV_u = Pd^T_u dO, dK_u = dS^T_u Q (K dimension = queries: A = the K-major tiles the element-wise warps
+                    // wrote, B = dO / Q rows, MN-major) and dQ_m += dS[queries of tile m, keys of tile u] K_u (A = the dS^T
+                    // tile read MN-major: 64-query blocks P_CHUNK_BYTES apart, 16 key rows per K step; B = K rows of tile
+                    // u, MN-major): up to four independent accumulators, one K step of each per round
+                    {
+                        const int nq = SP / 16;
+                        const int ksteps = (u == 0 ? (SP < 128 ? SP : 128) : SP - 128) / 16;
+                        const uint64_t b_do = ptx::smem_desc_sw128(sdO, 8192u, 1024u), b_q = ptx::smem_desc_sw128(sQ, 8192u, 1024u);
+                        const uint64_t b_k = ptx::smem_desc_sw128(sK + u * 16384u, 8192u, 1024u);
+                        const uint64_t a_dq0 = ptx::smem_desc_sw128(sDS, P_CHUNK_BYTES, 1024u);
+                        const uint64_t a_dq1 = ptx::smem_desc_sw128(sDS + 2u * P_CHUNK_BYTES, P_CHUNK_BYTES, 1024u);
+                        const int rounds = nq > ksteps ? nq : ksteps;
+                        for (int kk = 0; kk < rounds; ++kk) {
+                            if (kk < nq) {
+                                const uint32_t a_off = (kk >> 2) * P_CHUNK_BYTES + (kk & 3) * 32u;
+                                ptx::umma_bf16(tmem_base + TMB_DV, ptx::smem_desc_sw128(sPD + a_off, 16u, 1024u),
+                                               b_do + 128u * kk, idesc_kv, kk > 0 ? 1u : 0u);
+                                ptx::umma_bf16(tmem_base + TMB_DK, ptx::smem_desc_sw128(sDS + a_off, 16u, 1024u),
+                                               b_q + 128u * kk, idesc_kv, kk > 0 ? 1u : 0u);
+                            }
+                            if (kk < ksteps) {
+                                const uint32_t acc = (u > 0 || kk > 0) ? 1u : 0u;
+                                ptx::umma_bf16(tmem_base + TMB_DQ, a_dq0 + 128u * kk, b_k + 128u * kk, idesc_dq, acc);
+                                if (nu == 2)
+                                    ptx::umma_bf16(tmem_base + TMB_DQ + 64u, a_dq1 + 128u * kk, b_k + 128u * kk, idesc_dq, acc);
+                            }
+                        }
                     }
-                    for (int kk = 0; kk < SP / 16; ++kk) {
-                        const uint32_t a_off = (kk >> 2) * P_CHUNK_BYTES + (kk & 3) * 32u;
-                        ptx::umma_bf16(tmem_base + TMB_DK, ptx::smem_desc_sw128(sDS + a_off, 16u, 1024u),
-                                       ptx::smem_desc_sw128(sQ + kk * 2048u, 8192u, 1024u), idesc_kv, kk > 0 ? 1u : 0u);
-                    }
-                    // dQ_m += dS[queries of tile m, keys of tile u] K_u: A is the dS^T tile read MN-major (64-query
-                    // blocks P_CHUNK_BYTES apart, 16 key rows per K step), B = K rows of tile u, MN-major
-                    const int ksteps = (u == 0 ? (SP < 128 ? SP : 128) : SP - 128) / 16;
-                    for (int m = 0; m < nu; ++m)
-                        for (int kk = 0; kk < ksteps; ++kk)
-                            ptx::umma_bf16(tmem_base + TMB_DQ + m * 64u,
-                                           ptx::smem_desc_sw128(sDS + m * 2u * P_CHUNK_BYTES + kk * 2048u, P_CHUNK_BYTES, 1024u),
-                                           ptx::smem_desc_sw128(sK + u * 16384u + kk * 2048u, 8192u, 1024u), idesc_dq,
-                                           (u > 0 || kk > 0) ? 1u : 0u);
                     ptx::umma_commit(kv_full(u));
+                    pc.lap(6);
                 }
                 ptx::umma_commit(ld_empty);
                 ptx::umma_commit(dq_full);
@@ -711,26 +754,35 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
         const int nch = SP / 16, per = (nch + NSPLIT - 1) / NSPLIT;          // 16-column chunks per part
         const int c_begin = min(part * per, nch) * 16, c_end = min((part + 1) * per, nch) * 16;
+        PhaseClock pc(p.prof, bwd_threads(NSPLIT) / 32);
         int it = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
             const uint32_t itp = it & 1u;
             const int b = item / NH, h = item - b * NH;
             const long long row0 = (long long)b * S;
+            pc.lap(0);
             // ---- per-query vectors: lse in the exp2 domain (+inf for padding columns -> P = 0), delta
             float* lse2 = vec + (it & 1) * 2 * SP;
             float* delta = lse2 + SP;
             {
                 const float* Lg = p.lse + ((long long)b * NH + h) * S;
                 for (int i = threadIdx.x - 64; i < SP; i += 128 * NSPLIT) lse2[i] = i < S ? Lg[i] * LOG2E : INFINITY;
+                // delta = rowsum(dO * O) from the two TMA tiles: both carry the same 128-byte swizzle, so the products of
+                // matching 16-byte units sum to the row's dot product whatever the unit order is
+                ptx::mbar_wait(ld_full, itp);
+                pc.lap(1);
                 for (int r0 = ew * 4; r0 < SP; r0 += 16 * NSPLIT) {
-                    const int r = r0 + (lane >> 3), c8 = (lane & 7) * 8;
+                    const int r = r0 + (lane >> 3), off = r * 128 + (lane & 7) * 16;
                     float acc = 0.f;
-                    if (r < S) {
-                        float a[8], d[8];
-                        load8_bf16(p.ctx + (row0 + r) * HID + h * HD + c8, a);
-                        load8_bf16(p.dctx + (row0 + r) * HID + h * HD + c8, d);
+                    if (r < SP) {
+                        const uint4 ua = *reinterpret_cast<const uint4*>(gO + off);
+                        const uint4 ud = *reinterpret_cast<const uint4*>(gdO + off);
+                        const uint32_t a[4] = {ua.x, ua.y, ua.z, ua.w}, d[4] = {ud.x, ud.y, ud.z, ud.w};
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) acc = fmaf(a[k], d[k], acc);
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 fa = unpack_bf16(a[k]), fd = unpack_bf16(d[k]);
+                            acc = fmaf(fa.x, fd.x, fmaf(fa.y, fd.y, acc));
+                        }
                     }
                     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -746,34 +798,45 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 const int key = u * 128 + kr;
                 const bool key_ok = key < S;
                 const float bias = key_ok ? (p.mask[row0 + key] != 0 ? 0.f : MASK_LOG2) : -INFINITY;
+                pc.lap(0);
                 ptx::mbar_wait(sd_full(u), itp);
+                pc.lap(2);
                 ptx::tc_fence_after();
                 const uint32_t prow = static_cast<uint32_t>(kr) * 128u;
+                // dropout (common.cuh "Attention-probability dropout"): this thread's key contributes CB^(key & 15)
+                const uint32_t bpow = drop_pow_rt(DROP_CB, static_cast<uint32_t>(key)), jblk = static_cast<uint32_t>(key) >> 4;
+                const uint32_t t32 = p.drop.thresh << 16;
                 for (int c = c_begin; c < c_end; c += 16) {
                     uint32_t rs[16], rd[16], pd[8], ds[8];
                     ptx::tmem_ld_32x16(tmem_base + lane_sel + TMB_S + c, rs);
                     ptx::tmem_ld_32x16(tmem_base + lane_sel + TMB_DP + c, rd);
+                    const uint32_t rbase = p.drop.thresh ? drop_block_hash(hkey, static_cast<uint32_t>(c) >> 4, jblk) * bpow : 0u;
                     ptx::tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const float2 l2 = *reinterpret_cast<const float2*>(lse2 + c + j);
-                        const float2 de = *reinterpret_cast<const float2*>(delta + c + j);
-                        const float p0 = fast_ex2(fmaf(__uint_as_float(rs[j]), SCALE_LOG2, bias) - l2.x);
-                        const float p1 = fast_ex2(fmaf(__uint_as_float(rs[j + 1]), SCALE_LOG2, bias) - l2.y);
-                        float pd0 = p0, pd1 = p1, dp0 = __uint_as_float(rd[j]), dp1 = __uint_as_float(rd[j + 1]);
-                        if (p.drop.thresh) {
-                            // element (query c + j, key): the same counter stream as the forward (idx = query * S + key)
-                            const uint32_t i0 = static_cast<uint32_t>(c + j) * static_cast<uint32_t>(S) + key;
-                            const bool k0 = drop_keep(hkey, i0, p.drop.thresh);
-                            const bool k1 = drop_keep(hkey, i0 + static_cast<uint32_t>(S), p.drop.thresh);
-                            const float s0 = k0 ? p.drop.scale : 0.f, s1 = k1 ? p.drop.scale : 0.f;   // finite operands only
-                            pd0 = p0 * s0; dp0 *= s0;
-                            pd1 = p1 * s1; dp1 *= s1;
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c + j);
+                        const float4 d4 = *reinterpret_cast<const float4*>(delta + c + j);
+                        const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq[4] = {d4.x, d4.y, d4.z, d4.w};
+                        float pdv[4], dsv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float pe = fast_ex2(fmaf(__uint_as_float(rs[j + e]), SCALE_LOG2, bias) - lq[e]);
+                            float dp = __uint_as_float(rd[j + e]);
+                            pdv[e] = pe;
+                            if (p.drop.thresh) {
+                                // element (query c + j + e, key): same stream as the forward
+                                const float sc = rbase * drop_pow(DROP_CA, j + e) >= t32 ? p.drop.scale : 0.f;   // finite operands only
+                                pdv[e] = pe * sc;
+                                dp *= sc;
+                            }
+                            // dS without the 1/sqrt(64): a power of two commutes with the bf16 rounding, so it is applied
+                            // once per OUTPUT element in the dK / dQ epilogues instead of once per score here
+                            dsv[e] = pe * (dp - dq[e]);
                         }
-                        pd[j / 2] = pack_bf16(pd0, pd1);
-                        // dS without the 1/sqrt(64): a power of two commutes with the bf16 rounding, so it is applied
-                        // once per OUTPUT element in the dK / dQ epilogues instead of once per score here
-                        ds[j / 2] = pack_bf16(p0 * (dp0 - de.x), p1 * (dp1 - de.y));
+                        pd[j / 2] = pack_bf16(pdv[0], pdv[1]);
+                        pd[j / 2 + 1] = pack_bf16(pdv[2], pdv[3]);
+                        ds[j / 2] = pack_bf16(dsv[0], dsv[1]);
+                        ds[j / 2 + 1] = pack_bf16(dsv[2], dsv[3]);
                     }
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
@@ -787,9 +850,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(pds_full(u));
+                pc.lap(3);
 
                 // this key row's [dV_u | dK_u] = TMEM columns [0,128): part -> a 128 / NSPLIT-column slice -> dqkv
                 ptx::mbar_wait(kv_full(u), itp);
+                pc.lap(4);
                 ptx::tc_fence_after();
                 constexpr int WKV = 128 / NSPLIT;
                 const int ckv = part * WKV;
@@ -798,11 +863,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(s_empty(u));
+                pc.lap(5);
             }
 
             // dQ: query rows in the lanes; part = which 64 / NSPLIT of the 64 columns
             if (q * 32 < S) {
+                pc.lap(0);
                 ptx::mbar_wait(dq_full, itp);
+                pc.lap(6);
                 ptx::tc_fence_after();
                 constexpr int WQ = HD / NSPLIT;
                 store_cols<WQ>(tmem_base + lane_sel + TMB_DQ + part * WQ,
@@ -813,6 +881,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(dq_empty);
+                pc.lap(7);
             }
         }
     }
@@ -837,8 +906,8 @@ std::atomic<int> g_tc_enabled{-1};      // -1: not decided yet (environment), 0 
 bool attn_tc_enabled() {
     int v = g_tc_enabled.load(std::memory_order_relaxed);
     if (v < 0) {
-        const char* e = getenv("UC2_ATTN_TCGEN05");
-        v = (e && e[0] == '1') ? 1 : 0;
+        const char* e = getenv("UC2_ATTN_TCGEN05");          // on unless UC2_ATTN_TCGEN05=0
+        v = (e && e[0] == '0') ? 0 : 1;
         g_tc_enabled.store(v, std::memory_order_relaxed);
     }
     return v == 1;
@@ -938,16 +1007,17 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     UC2_REQUIRE(SP <= TC_BWD_MAX_SP, UC2_ERR_UNSUPPORTED, "attention_bwd_tc: S=%d > %d", S, TC_BWD_MAX_SP);
     UC2_REQUIRE(aligned16(qkv) && aligned16(ctx) && aligned16(dctx) && (reinterpret_cast<uintptr_t>(dqkv) & 31) == 0,
                 UC2_ERR_ARG, "attention_bwd_tc: qkv / ctx / dctx must be 16-byte and dqkv 32-byte aligned");
-    CUtensorMap tq, tdo;
+    CUtensorMap tq, tdo, to;
     if (int rc = make_tmap(&tq, qkv, (long long)B * S, QKV_LD, QKV_LD, SP)) return rc;
     if (int rc = make_tmap(&tdo, dctx, (long long)B * S, HID, HID, SP)) return rc;
+    if (int rc = make_tmap(&to, ctx, (long long)B * S, HID, HID, SP)) return rc;
     const TcBwdSmem L = tc_bwd_smem(S, SP);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    static int nsplit = 2;
+    static int nsplit = 4;
     std::call_once(once, [] {
-        const char* e = getenv("UC2_ATTN_TC_BWD_SPLIT");          // tuning knob: 2 (default) or 4 warps per lane quarter
-        if (e && e[0] == '4') nsplit = 4;
+        const char* e = getenv("UC2_ATTN_TC_BWD_SPLIT");          // tuning knob: 4 (default) or 2 warps per lane quarter
+        if (e && e[0] == '2') nsplit = 2;
         const int bytes = static_cast<int>(tc_bwd_smem(TC_BWD_MAX_SP, TC_BWD_MAX_SP).total);
         attr_err = cudaFuncSetAttribute(attention_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (attr_err == cudaSuccess)
@@ -964,12 +1034,36 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     p.B = B; p.S = S; p.SP = SP; p.items = B * NH;
     p.drop = DropCfg{drop_key, drop_thresh, drop_scale};
     const int grid = p.items < num_sms() ? p.items : num_sms();
+    p.prof = nullptr;
+    static const bool prof_on = [] { const char* e = getenv("UC2_ATTN_PROF"); return e && e[0] == '1'; }();
+    static long long* prof_buf = nullptr;
+    const int prof_words = 148 * 32 * PROF_SLOTS;
+    if (prof_on) {
+        if (!prof_buf) cudaMalloc(&prof_buf, prof_words * sizeof(long long));
+        cudaMemsetAsync(prof_buf, 0, prof_words * sizeof(long long), (cudaStream_t)stream);
+        p.prof = prof_buf;
+    }
     ProfScope prof((cudaStream_t)stream, 1, 10.0 * B * NH * (double)S * S * HD);
     const cudaError_t e =
         nsplit == 4 ? launch_pdl(attention_bwd_tc_kernel<4>, dim3(grid), dim3(bwd_threads(4)), exclusive_smem(L.total),
-                                 (cudaStream_t)stream, 1, tq, tdo, p)
+                                 (cudaStream_t)stream, 1, tq, tdo, to, p)
                     : launch_pdl(attention_bwd_tc_kernel<2>, dim3(grid), dim3(bwd_threads(2)), exclusive_smem(L.total),
-                                 (cudaStream_t)stream, 1, tq, tdo, p);
+                                 (cudaStream_t)stream, 1, tq, tdo, to, p);
     UC2_REQUIRE(e == cudaSuccess, UC2_ERR_CUDA, "attention_bwd_tc launch failed: %s", cudaGetErrorString(e));
+    if (prof_on) {        // debug only: synchronises; prints the phase cycle counters of two CTAs
+        static int printed = 0;
+        cudaStreamSynchronize((cudaStream_t)stream);
+        if (printed++ < 4) {
+            const int W = bwd_threads(nsplit) / 32;
+            static long long host[148 * 32 * PROF_SLOTS];
+            cudaMemcpy(host, prof_buf, prof_words * sizeof(long long), cudaMemcpyDeviceToHost);
+            for (int c : {0, grid - 1})
+                for (int w = 0; w < W; ++w) {
+                    fprintf(stderr, "attn_bwd_tc prof B=%d S=%d drop=%u cta %d warp %d:", B, S, drop_thresh, c, w);
+                    for (int k = 0; k < PROF_SLOTS; ++k) fprintf(stderr, " %lld", host[((long long)c * W + w) * PROF_SLOTS + k]);
+                    fprintf(stderr, "\n");
+                }
+        }
+    }
     return check_last("attention_bwd_tc_kernel");
 }
