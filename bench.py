@@ -444,7 +444,8 @@ def run_training(args, workload, rank, world, steps, warmup, with_cpu, with_stor
               {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
     opt = AdamW(groups, lr=LR, betas=BETAS)
     step_fn = TrainStep(model, opt, grad_norm=GRAD_NORM,
-                        lr_fn=lambda s: max(LR * warmup_linear(s, WARMUP_STEPS, TRAIN_STEPS), 1e-8))
+                        lr_fn=lambda s: max(LR * warmup_linear(s, WARMUP_STEPS, TRAIN_STEPS), 1e-8),
+                        grad_comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else None)
 
     host = [(t, pin(b)) for t, b in host_batches(workload, 1000 + rank)]
     resident = [(t, UB.to_device(b, dev)) for t, b in host]
@@ -571,6 +572,7 @@ def run_training(args, workload, rank, world, steps, warmup, with_cpu, with_stor
             "config": {"workload": W["name"], "model": "uc2-base 12L/768H vocab 250002 random init",
                        "per_gpu_batch": per_gpu, "seq_len": S, "dropout": args.dropout, "weight_decay": WEIGHT_DECAY,
                        "gradient_accumulation_steps": 1,
+                       "parallelism": f"dp{world}" + (f", {args.grad_comm} gradient all-reduce (NCCL)" if world > 1 else ""),
                        "l2": "working set (1.1 GB fp32 params + >5 GB activations per step) far exceeds the 126 MB L2"},
             "e2e": {"value": per_gpu * world / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(np.mean([nbytes(b) for _, b in host])), "d2h_bytes_per_step": 4},
@@ -632,6 +634,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="hidden / attention dropout of the training workloads (config/uc2-base.json: 0.1)")
+    ap.add_argument("--grad-comm", default="bf16", choices=["bf16", "fp32"],
+                    help="wire type of the gradient exchange at N > 1 (the reference exchanges fp16 gradients)")
     ap.add_argument("--layers", type=int, default=12, help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -89,9 +89,25 @@ typedef struct {
      * kept values are multiplied by drop_scale.  drop_thresh = 0 disables it (uc2_b200/dropout.py has the rules). */
     unsigned int drop_key; unsigned int drop_thresh; float drop_scale;
     int tail_split;   /* 0 = auto (split the tiles of a partial last round into column slices); 1 = never */
+    /* Cross-entropy statistics fused into the epilogue (the tied MLM decoder, model/layer.py:257-265 followed by
+     * F.cross_entropy, model/model.py:592-596): with ce_stats != NULL the call must be  out_bf16 = A B^T + bias  and the
+     * epilogue also writes, per row m and per 32-column chunk c, the pair (max, sum exp(z - max)) of the fp32 values
+     * z = acc + bias of that chunk to ce_stats[(c * ld_ce + m) * 2 ..], and z[m, ce_labels[m]] to ce_tgt[m].
+     * uc2_ce_stats_reduce turns them into lse / loss; no fp32 [M, N] tensor is ever materialised. */
+    float* ce_stats; long long ld_ce; const long long* ce_labels; float* ce_tgt;
 } uc2_gemm_args;
 
 UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream);
+
+/* Second half of the fused cross entropy: per row, merge the n_chunks (max, sum-exp) pairs the GEMM epilogue left in
+ * stats ([n_chunks][ld_ce] pairs) into lse[row], and loss[row] = lse - tgt[row] (0 where targets[row] == ignore_index).
+ * part is a scratch of ceil(n_chunks / 256) * rows pairs. */
+UC2_API int uc2_ce_stats_reduce(const float* stats, long long ld_ce, int n_chunks, long long rows, const float* tgt,
+                                const long long* targets, long long ignore_index, float* part, float* loss, float* lse,
+                                void* stream);
+/* d(logits) in place over the bf16 logits: z <- dloss[row] * (exp(z - lse[row]) - [col == target]) (0 for ignored rows) */
+UC2_API int uc2_ce_bwd_inplace_bf16(void* logits_bf16, long long ld, long long rows, int C, const long long* targets,
+                                    long long ignore_index, const float* dloss, const float* lse, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Embeddings fused with the gather_index pack.
@@ -364,6 +380,41 @@ UC2_API int uc2_grad_sqnorm(const float* grad, const uc2_opt_chunk* chunks, int 
 UC2_API int uc2_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
                            const uc2_opt_chunk* chunks, int n_chunks, const int* act_step, const int* group_of,
                            const uc2_adamw_hyper* hyper, const double* sqnorm, void* stream);
+
+/* Deferred ("lazy") AdamW for one row-sparse table -- the 250 002 x 768 word-embedding table, 69 % of all parameters.
+ * A step whose only table gradient comes from the embedding lookup touches <= B*T rows, yet AdamW changes EVERY row
+ * (moment decay + decoupled weight decay: optim/adamw.py:77-101), 34 bytes per element of HBM traffic for the eager
+ * kernel.  Here a row's update is postponed until the row is needed -- it gets a gradient (uc2_adamw_lazy_rows), the
+ * forward reads it, or someone looks at the parameters (uc2_adamw_lazy_catchup) -- and then every postponed step is
+ * replayed on it in order with the identical fp32 operations and the identical per-step scalars (kept in a device
+ * ring `hist`, written by the same device code that the eager kernel uses to derive them), so parameters and moments
+ * end up BIT-IDENTICAL to eager AdamW while the rows stay in registers over the replay.
+ * row_step[r] = last optimizer step applied to row r; row_seen = scratch for duplicate ids (init -1). */
+typedef struct {
+    float* param; float* grad; float* exp_avg; float* exp_avg_sq;   /* arena bases */
+    long long table_off;      /* element offset of the table in the arenas */
+    int n_rows, width;        /* width must be a multiple of 4 */
+    int* row_step; int* row_seen;
+    float* hist; int hist_len;/* ring of (step_size, lr * weight_decay) pairs, entry t % hist_len belongs to step t */
+    float beta1, beta2, eps;
+    int decay_on;             /* the table's group has weight_decay > 0 (the eager kernel's `if (wd > 0)`) */
+    void* shadow_bf16;        /* base of the bf16 shadow arena (may be NULL): rows are re-cast whenever they change */
+} uc2_lazy_table;
+/* Step `step` (1-based) for the rows in row_ids (duplicates allowed, any order): replay what each row missed, apply
+ * this step with its gradient (times the clip coefficient derived from *sqnorm as uc2_adamw_step does), clear the
+ * gradient row.  first_step = the global step at which the table first had a gradient (bias correction counts from it). */
+UC2_API int uc2_adamw_lazy_rows(const uc2_lazy_table* t, const long long* row_ids, long long n_ids, int step,
+                                int first_step, float lr, float weight_decay, int correct_bias, float max_grad_norm,
+                                const double* sqnorm, void* stream);
+/* Record step `step`'s scalars in the ring WITHOUT touching any row (a step with no row list on this rank). */
+UC2_API int uc2_adamw_lazy_note(const uc2_lazy_table* t, int step, int first_step, float lr, float weight_decay,
+                                int correct_bias, void* stream);
+/* Bring rows up to date through step `upto` (row_ids == NULL: every row). */
+UC2_API int uc2_adamw_lazy_catchup(const uc2_lazy_table* t, const long long* row_ids, long long n_ids, int upto,
+                                   void* stream);
+/* *out += sum of squares of the gradient rows in row_ids, every distinct row once (mark = a value no earlier call used) */
+UC2_API int uc2_grad_sqnorm_rows(const uc2_lazy_table* t, const long long* row_ids, long long n_ids, int mark,
+                                 double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Device-side batch assembly (the step before the path) for region features that are

@@ -22,7 +22,8 @@ class GemmArgs(C.Structure):
                 ("aux", P), ("ld_aux", LL), ("act", I), ("out_bf16", P), ("ld_out", LL),
                 ("out_pre", P), ("ld_pre", LL), ("out_f32", P), ("ld_f32", LL),
                 ("accumulate", I), ("split_k", I), ("block_n", I), ("residual_f32", I), ("ctas", I),
-                ("drop_key", C.c_uint), ("drop_thresh", C.c_uint), ("drop_scale", F), ("tail_split", I)]
+                ("drop_key", C.c_uint), ("drop_thresh", C.c_uint), ("drop_scale", F), ("tail_split", I),
+                ("ce_stats", P), ("ld_ce", LL), ("ce_labels", P), ("ce_tgt", P)]
 
 
 class EmbedArgs(C.Structure):
@@ -71,6 +72,12 @@ class OptChunk(C.Structure):
     _fields_ = [("offset", LL), ("n", I), ("tensor", I)]
 
 
+class LazyTable(C.Structure):
+    _fields_ = [("param", P), ("grad", P), ("exp_avg", P), ("exp_avg_sq", P), ("table_off", LL), ("n_rows", I),
+                ("width", I), ("row_step", P), ("row_seen", P), ("hist", P), ("hist_len", I),
+                ("beta1", F), ("beta2", F), ("eps", F), ("decay_on", I), ("shadow_bf16", P)]
+
+
 class AdamwHyper(C.Structure):
     _fields_ = [("lr", F * 8), ("weight_decay", F * 8), ("beta1", F), ("beta2", F), ("eps", F),
                 ("correct_bias", I), ("global_step", I), ("max_grad_norm", F), ("zero_grad", I)]
@@ -108,6 +115,8 @@ _SIGS = {
     "uc2_softmax_loss": [P, LL, LL, I, I, P, LL, P, P, P, P, P, P],
     "uc2_mse": [P, P, P, P, P, LL, P],
     "uc2_ce_loss_fwd": [P, LL, LL, I, P, LL, P, P, P],
+    "uc2_ce_stats_reduce": [P, LL, I, LL, P, P, LL, P, P, P, P],
+    "uc2_ce_bwd_inplace_bf16": [P, LL, LL, I, P, LL, P, P, P],
     "uc2_ce_loss_bwd_bf16": [P, LL, LL, I, P, LL, P, P, P, LL, P],
     "uc2_mask_scan": [P, LL, P, P, I, P],
     "uc2_gather_rows": [P, P, P, I, I, P, I, P],
@@ -123,6 +132,10 @@ _SIGS = {
     "uc2_cast_f32_bf16": [P, P, LL, P],
     "uc2_grad_sqnorm": [P, P, I, P, P, P],
     "uc2_adamw_step": [P, P, P, P, P, P, I, P, P, C.POINTER(AdamwHyper), P, P],
+    "uc2_adamw_lazy_rows": [C.POINTER(LazyTable), P, LL, I, I, F, F, I, F, P, P],
+    "uc2_adamw_lazy_note": [C.POINTER(LazyTable), I, I, F, F, I, P],
+    "uc2_adamw_lazy_catchup": [C.POINTER(LazyTable), P, LL, I, P],
+    "uc2_grad_sqnorm_rows": [C.POINTER(LazyTable), P, LL, I, P, P],
 }
 EXPORTS = sorted(list(_SIGS) + ["uc2_last_error", "uc2_version", "uc2_launch_count", "uc2_attention_tc_enable",
                                 "uc2_encoder_bwd_workspace_bytes", "uc2_encoder_fwd_workspace_bytes"])
@@ -193,7 +206,7 @@ def launch_count():
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None, residual=None, aux=None,
          act=ACT_NONE, out_bf16=None, out_pre=None, out_f32=None, accumulate=False, split_k=1, block_n=0,
-         ld_out=None, ld_res=None, ctas=0, drop=None, tail_split=0):
+         ld_out=None, ld_res=None, ctas=0, drop=None, tail_split=0, ce=None):
     """D[M,N] = A[M,K] @ B[N,K]^T with the fused epilogue described in include/uc2_b200.h."""
     g = GemmArgs()
     g.a, g.lda, g.a_mn = a.data_ptr(), (lda if lda is not None else a.stride(0)), int(a_mn)
@@ -214,6 +227,9 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None
         g.out_f32, g.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
     g.accumulate, g.split_k, g.block_n, g.ctas = int(accumulate), split_k, block_n, ctas
     g.tail_split = tail_split
+    if ce is not None:                     # (stats [n_chunks, ld_ce, 2] fp32, labels int64 [M], target logits fp32 [M])
+        stats, labels, tgt = ce
+        g.ce_stats, g.ld_ce, g.ce_labels, g.ce_tgt = stats.data_ptr(), stats.stride(0) // 2, labels.data_ptr(), tgt.data_ptr()
     if drop is not None:
         g.drop_key, g.drop_thresh, g.drop_scale = drop
     check(lib().uc2_gemm_bf16(C.byref(g), stream()), "gemm")

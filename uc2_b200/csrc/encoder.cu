@@ -30,7 +30,7 @@ struct G {
 };
 
 int run(cudaStream_t s, const G& g) {
-    uc2_gemm_args a;
+    uc2_gemm_args a = {};          // every field this file does not set (the fused-CE ones) stays null
     a.a = g.a; a.lda = g.lda; a.a_mn = g.a_mn; a.b = g.b; a.ldb = g.ldb; a.b_mn = g.b_mn;
     a.M = g.M; a.N = g.N; a.K = g.K; a.bias = g.bias; a.residual = g.residual; a.ld_res = g.ld_res;
     a.aux = g.aux; a.ld_aux = g.ld_aux; a.act = g.act; a.out_bf16 = g.out_bf16; a.ld_out = g.ld_out;

@@ -76,6 +76,8 @@ struct GemmParams {
     // costs ~1/tail_split of a full one (19200 tokens = 75 row blocks on 74 CTA pairs would otherwise pay a whole
     // extra round for 1-4 % of the work).  tail_split == 1: off.
     int tail_start, tail_split;
+    // MODE 9: cross-entropy statistics per (row, 32-column chunk), see uc2_gemm_args
+    float2* ce_stats; long long ce_ld; const long long* ce_labels; float* ce_tgt;
 };
 
 struct TileCoord { int m_blk, n0, width, split; };
@@ -122,10 +124,11 @@ __device__ __forceinline__ void store_bf16_row16(bf16* dst, const float* v) {
 //   6 wgrad          : fp32 atomic accumulate
 //   7 O-proj dgrad   : plain                                             -> bf16
 //   8 O-proj / FFN2  : dropout(+ bias) + fp32 residual (training)        -> fp32
+//   9 MLM decoder    : + bias -> bf16 logits, and (max, sum-exp) per row and 32-column chunk + the target logit
 template <int MODE>
 struct Epi {
     static __device__ __forceinline__ bool bias(const GemmParams& p) {
-        return MODE == 0 ? p.bias != nullptr : (MODE == 1 || MODE == 3 || MODE == 4 || MODE == 8);
+        return MODE == 0 ? p.bias != nullptr : (MODE == 1 || MODE == 3 || MODE == 4 || MODE == 8 || MODE == 9);
     }
     static __device__ __forceinline__ bool out_pre(const GemmParams& p) { return MODE == 0 ? p.out_pre != nullptr : MODE == 1; }
     static __device__ __forceinline__ int act(const GemmParams& p) {
@@ -135,7 +138,8 @@ struct Epi {
         return MODE == 0 ? p.residual != nullptr : (MODE == 3 || MODE == 5 || MODE == 8);
     }
     static __device__ __forceinline__ bool out_bf16(const GemmParams& p) {
-        return MODE == 0 ? p.out_bf16 != nullptr : (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 7);
+        return MODE == 0 ? p.out_bf16 != nullptr
+                         : (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 7 || MODE == 9);
     }
     static __device__ __forceinline__ bool out_f32(const GemmParams& p) {
         return MODE == 0 ? p.out_f32 != nullptr : (MODE == 3 || MODE == 6 || MODE == 8);
@@ -189,6 +193,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
     constexpr int G = MY < 2 ? MY : 2;               // chunks per group
     constexpr int W = EX == 2 ? 32 : 16;             // 32-bit words of the extra operand per chunk row
     const bool row_ok = grow < p.M;
+    // MODE 9: running (max, sum exp) of this row over the two halves of a chunk, and the row's label
+    float ce_m = 0.f, ce_s = 0.f;
+    const int ce_t = (MODE == 9 && row_ok) ? static_cast<int>(p.ce_labels[grow]) : -1;
     uint32_t pf[EX == 0 ? 1 : G * W];
     const bf16* exb = F::residual(p) ? p.residual : p.aux;
     const long long ld_ex = F::residual(p) ? p.ld_res : p.ld_aux;
@@ -248,6 +255,25 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
                             v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                         }
+                    }
+                    if (MODE == 9) {
+                        constexpr float L2E = 1.4426950408889634f;
+                        float cm = v[0];
+#pragma unroll
+                        for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[j]);
+                        const float nm = h == 0 ? cm : fmaxf(ce_m, cm), nml = nm * L2E;
+                        float ss = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) ss += fast_ex2(fmaf(v[j], L2E, -nml));
+                        ce_s = h == 0 ? ss : fmaf(ce_s, fast_ex2(fmaf(ce_m, L2E, -nml)), ss);
+                        ce_m = nm;
+                        if (static_cast<unsigned>(ce_t - col0) < 16u) {          // the label's own logit, in fp32
+                            float z = v[0];
+#pragma unroll
+                            for (int j = 1; j < 16; ++j) z = (ce_t - col0 == j) ? v[j] : z;
+                            p.ce_tgt[grow] = z;
+                        }
+                        if (h == 1) p.ce_stats[static_cast<long long>(col0 >> 5) * p.ce_ld + grow] = make_float2(ce_m, ce_s);
                     }
                     if (F::out_pre(p)) store_bf16_row16(p.out_pre + grow * p.ld_pre + col0, v);
                     if (F::act(p) == UC2_ACT_GELU) {
@@ -340,7 +366,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                     float loc[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) loc[j] = __uint_as_float(r[j]);
-                    if (row_ok) epilogue_scalar_row(p, loc, grow, col0);
+                    if (MODE == 9) {
+                        // the chunk that holds column N - 1: same outputs, element by element
+                        if (row_ok) {
+#pragma unroll 1
+                            for (int j = 0; j < 16 && col0 + j < p.N; ++j) {
+                                const float z = loc[j] + p.bias[col0 + j];
+                                p.out_bf16[grow * p.ld_out + col0 + j] = __float2bfloat16(z);
+                                if (h == 0 && j == 0) {
+                                    ce_m = z;
+                                    ce_s = 1.f;
+                                } else {
+                                    const float nm = fmaxf(ce_m, z);
+                                    ce_s = ce_s * __expf(ce_m - nm) + __expf(z - nm);
+                                    ce_m = nm;
+                                }
+                                if (col0 + j == ce_t) p.ce_tgt[grow] = z;
+                            }
+                            if (h == 1 || col0 + 16 >= p.N)
+                                p.ce_stats[static_cast<long long>(col0 >> 5) * p.ce_ld + grow] = make_float2(ce_m, ce_s);
+                        }
+                    } else if (row_ok) {
+                        epilogue_scalar_row(p, loc, grow, col0);
+                    }
                 }
             }
         }
@@ -744,6 +792,7 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
     p.out_f32 = a.out_f32; p.ld_f32 = a.ld_f32;
     p.accumulate = a.accumulate;
     p.drop.key = a.drop_key; p.drop.thresh = a.drop_thresh; p.drop.scale = a.drop_scale;
+    p.ce_stats = reinterpret_cast<float2*>(a.ce_stats); p.ce_ld = a.ld_ce; p.ce_labels = a.ce_labels; p.ce_tgt = a.ce_tgt;
     UC2_REQUIRE(a.drop_thresh < 65536u, UC2_ERR_ARG, "uc2_gemm_bf16: drop_thresh must be < 65536");
     // 256-bit row slices: 32-byte aligned bases, pitches that keep every row 32-byte aligned
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
@@ -754,6 +803,18 @@ extern "C" UC2_API int uc2_gemm_bf16(const uc2_gemm_args* args, void* stream) {
                (!a.out_f32 || (a.ld_f32 % 8 == 0 && al32(a.out_f32))) && (!a.bias || aligned16(a.bias));
     p.num_n_blocks = (a.N + bn - 1) / bn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (a.ce_stats) {
+        // MLM decoder + cross-entropy statistics (MODE 9): bf16 logits = A B^T + bias, nothing else
+        UC2_REQUIRE(a.ce_labels && a.ce_tgt && a.ld_ce >= a.M && (reinterpret_cast<uintptr_t>(a.ce_stats) & 7) == 0,
+                    UC2_ERR_ARG, "uc2_gemm_bf16: ce_stats needs ce_labels, ce_tgt and ld_ce >= M");
+        UC2_REQUIRE(!a.a_mn && !a.b_mn && a.bias && a.out_bf16 && !a.out_f32 && !a.out_pre && !a.residual && !a.aux &&
+                        a.act == UC2_ACT_NONE && a.drop_thresh == 0 && split_k == 1 && p.vec_ok,
+                    UC2_ERR_ARG, "uc2_gemm_bf16: ce_stats goes with out_bf16 = A B^T + bias only (32-byte aligned rows)");
+        p.num_m_blocks = (a.M + BLOCK_M * (a.M > BLOCK_M ? 2 : 1) - 1) / (BLOCK_M * (a.M > BLOCK_M ? 2 : 1));
+        p.num_n_blocks = (a.N + 255) / 256;
+        if (a.M > BLOCK_M) return launch<256, false, false, 2, 9>(a, p, s);
+        return launch<256, false, false, 1, 9>(a, p, s);
+    }
     if (ctas == 2 && bn == 256 && p.vec_ok) {
         // the BertLayer stack's own epilogues, compiled without run-time switches (see Epi<MODE>)
         const bool bf = a.out_bf16 && !a.out_f32, f32o = a.out_f32 && !a.out_bf16;

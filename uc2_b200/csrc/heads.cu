@@ -236,6 +236,83 @@ ce_loss_bwd_kernel(const float* __restrict__ logits, long long ld, int C, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused cross entropy, second half: the decoder GEMM (gemm_tcgen05.cu, MODE 9) leaves one (max, sum exp(z - max))
+// pair per row and 32-column chunk in stats[chunk][row]; merge them per row.  Level 1: a CTA takes 32 rows x 256
+// chunks (lane = row, so every warp access is 256 contiguous bytes; warp = 32 of the chunks), level 2: one thread
+// per row over the <= 31 partials, then lse and loss = lse - target logit (model/model.py:592-596).
+// ------------------------------------------------------------------------------------------------
+constexpr int CE_L1_CHUNKS = 256;
+
+__device__ __forceinline__ void ce_merge(float& m, float& s, float m2, float s2) {
+    const float mm = fmaxf(m, m2);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mm)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mm));
+    m = mm;
+}
+
+__global__ void __launch_bounds__(256)
+ce_stats_l1_kernel(const float2* __restrict__ stats, long long ld, int n_chunks, long long rows, float2* __restrict__ part) {
+    __shared__ float2 red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = (long long)blockIdx.y * 32 + lane;
+    const int c0 = blockIdx.x * CE_L1_CHUNKS + warp * 32;
+    float m = -INFINITY, s = 0.f;
+    if (row < rows) {
+        const int c1 = min(c0 + 32, n_chunks);
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) {
+            const float2 v = __ldg(stats + (long long)c * ld + row);
+            ce_merge(m, s, v.x, v.y);
+        }
+    }
+    red[warp][lane] = make_float2(m, s);
+    __syncthreads();
+    if (warp == 0 && row < rows) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) ce_merge(m, s, red[w][lane].x, red[w][lane].y);
+        part[(long long)blockIdx.x * rows + row] = make_float2(m, s);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+ce_stats_l2_kernel(const float2* __restrict__ part, int n_part, long long rows, const float* __restrict__ tgt,
+                   const long long* __restrict__ targets, long long ignore_index, float* __restrict__ loss,
+                   float* __restrict__ lse_out) {
+    const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (row >= rows) return;
+    float m = -INFINITY, s = 0.f;
+    for (int k = 0; k < n_part; ++k) {
+        const float2 v = part[(long long)k * rows + row];
+        ce_merge(m, s, v.x, v.y);
+    }
+    const float lse = m + logf(s);
+    lse_out[row] = lse;
+    if (loss) loss[row] = targets[row] == ignore_index ? 0.f : lse - tgt[row];
+}
+
+// d(logits) over the bf16 logits, in place (8 columns per thread)
+__global__ void __launch_bounds__(256)
+ce_bwd_inplace_kernel(bf16* __restrict__ z, long long ld, int C, const long long* __restrict__ targets,
+                      long long ignore_index, const float* __restrict__ dloss, const float* __restrict__ lse) {
+    const long long r = blockIdx.y;
+    bf16* x = z + r * ld;
+    const long long t = targets[r];
+    const float g = (t == ignore_index) ? 0.f : dloss[r];
+    const float l = lse[r];
+    const int c0 = (blockIdx.x * 256 + threadIdx.x) * 8;
+    if (c0 >= C) return;
+    if (c0 + 8 <= C) {
+        float v[8];
+        load8_bf16(x + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = g * (__expf(v[j] - l) - ((long long)(c0 + j) == t ? 1.f : 0.f));
+        store8_bf16(x + c0, v);
+    } else {
+        for (int c = c0; c < C; ++c)
+            x[c] = __float2bfloat16(g * (__expf(__bfloat162float(x[c]) - l) - ((long long)c == t ? 1.f : 0.f)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // order-exact masked-row compaction (hidden[mask], model/model.py:653-657), no host sync:
 //   pass 1 (one CTA): exclusive scan of the mask in row-major (b, j) order -> index list + count
 //   pass 2: gather rows / scatter-add gradient rows
@@ -416,6 +493,38 @@ extern "C" UC2_API int uc2_ce_loss_bwd_bf16(const float* logits, long long ld, l
     ce_loss_bwd_kernel<<<dim3((C + 1023) / 1024, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
         logits, ld, C, targets, ignore_index, dloss, lse, (bf16*)dlogits_bf16, ld_out);
     return check_last("ce_loss_bwd_kernel");
+}
+
+extern "C" UC2_API int uc2_ce_stats_reduce(const float* stats, long long ld_ce, int n_chunks, long long rows,
+                                           const float* tgt, const long long* targets, long long ignore_index,
+                                           float* part, float* loss, float* lse, void* stream) {
+    if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(stats && tgt && targets && part && lse && n_chunks > 0 && rows >= 0 && ld_ce >= rows &&
+                    (reinterpret_cast<uintptr_t>(stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(part) & 7) == 0,
+                UC2_ERR_ARG, "ce_stats_reduce: bad args");
+    if (rows == 0) return UC2_OK;
+    const int n_part = (n_chunks + CE_L1_CHUNKS - 1) / CE_L1_CHUNKS;
+    UC2_REQUIRE((rows + 31) / 32 < 65536, UC2_ERR_UNSUPPORTED, "ce_stats_reduce: too many rows");
+    ce_stats_l1_kernel<<<dim3(n_part, (unsigned)((rows + 31) / 32)), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(stats), ld_ce, n_chunks, rows, reinterpret_cast<float2*>(part));
+    if (int rc = check_last("ce_stats_l1_kernel")) return rc;
+    ce_stats_l2_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(part), n_part, rows, tgt, targets, ignore_index, loss, lse);
+    return check_last("ce_stats_l2_kernel");
+}
+
+extern "C" UC2_API int uc2_ce_bwd_inplace_bf16(void* logits_bf16, long long ld, long long rows, int C,
+                                               const long long* targets, long long ignore_index, const float* dloss,
+                                               const float* lse, void* stream) {
+    if (int rc = require_sm100()) return rc;
+    UC2_REQUIRE(logits_bf16 && targets && dloss && lse && rows >= 0 && C > 0 && ld >= C && ld % 8 == 0 &&
+                    aligned16(logits_bf16),
+                UC2_ERR_ARG, "ce_bwd_inplace: bad args (ld must be a multiple of 8, base 16-byte aligned)");
+    UC2_REQUIRE(rows < 65536, UC2_ERR_UNSUPPORTED, "ce_bwd_inplace: at most 65535 rows per call");
+    if (rows == 0) return UC2_OK;
+    ce_bwd_inplace_kernel<<<dim3((C + 2047) / 2048, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(
+        (bf16*)logits_bf16, ld, C, targets, ignore_index, dloss, lse);
+    return check_last("ce_bwd_inplace_kernel");
 }
 
 extern "C" UC2_API int uc2_mask_scan(const unsigned char* mask, long long n, int* index, int* count, int capacity,

@@ -83,15 +83,33 @@ class _DivAfter(object):
 
 
 class GradSync(object):
-    """Bucketed, backward-overlapped gradient averaging over a flat gradient arena."""
+    """Bucketed, backward-overlapped gradient averaging over a flat gradient arena.
 
-    def __init__(self, flat_grad, bucket_bytes=64 << 20):
+    comm_dtype (CUDA only): exchange the gradients in this 16-bit type instead of the arena's fp32 -- what the
+    reference itself does (apex O2 hands fp16 gradients to all_reduce_and_rescale_tensors, utils/distributed.py:15-42,
+    2 bytes per gradient on the wire).  A bucket is cast into a persistent communication buffer, averaged there, and
+    cast back into the fp32 arena in finish(); accumulation over ranks happens inside NCCL."""
+
+    def __init__(self, flat_grad, bucket_bytes=64 << 20, comm_dtype=None):
         self.flat = flat_grad
         self.bucket = max(1, bucket_bytes // flat_grad.element_size())
         self.works = []
         self.enabled = True
         self.allow_sparse = False   # row-sparse exchange is only valid when one backward pass feeds the step
         self.done = []          # [lo, hi) ranges already submitted in this step
+        self.comm_dtype = comm_dtype if (comm_dtype is not None and flat_grad.is_cuda) else None
+        self.comm = None        # persistent 16-bit staging buffer, same indexing as flat
+        self.staged = []        # (work, lo, hi) buckets to copy back in finish()
+
+    def _submit(self, s, e):
+        if self.comm_dtype is None:
+            self.works.append(_avg_inplace(self.flat[s:e], async_op=True))
+            return
+        if self.comm is None:
+            self.comm = torch.empty(self.flat.numel(), dtype=self.comm_dtype, device=self.flat.device)
+        buf = self.comm[s:e]
+        buf.copy_(self.flat[s:e])
+        self.staged.append((dist.all_reduce(buf, op=dist.ReduceOp.AVG, async_op=True), s, e))
 
     def ready(self, lo, hi):
         """The backward pass has finished writing flat[lo:hi]."""
@@ -99,7 +117,7 @@ class GradSync(object):
             return
         self.done.append((lo, hi))
         for s in range(lo, hi, self.bucket):
-            self.works.append(_avg_inplace(self.flat[s:min(s + self.bucket, hi)], async_op=True))
+            self._submit(s, min(s + self.bucket, hi))
 
     def sparse_rows_table(self, lo, n_rows, width, row_ids, pad_row=0):
         """sparse_rows() for a table of exactly n_rows rows starting at flat[lo]."""
@@ -107,7 +125,9 @@ class GradSync(object):
             return
         sub = GradSync.__new__(GradSync)
         sub.flat, sub.bucket, sub.works, sub.enabled, sub.done = self.flat[:lo + n_rows * width], self.bucket, [], True, []
+        sub.comm_dtype = self.comm_dtype
         sub.sparse_rows(lo, width, row_ids, pad_row)
+        self.last_ids = sub.last_ids
         self.done.append((lo, lo + n_rows * width))
 
     def sparse_rows(self, lo, width, row_ids, pad_row=0):
@@ -131,12 +151,15 @@ class GradSync(object):
         n_rows = (self.flat.numel() - lo) // width
         table = self.flat[lo:lo + n_rows * width].view(n_rows, width)
         rows = table.index_select(0, ids) * first.unsqueeze(1).to(table.dtype)     # each local row once
+        if getattr(self, "comm_dtype", None) is not None:
+            rows = rows.to(self.comm_dtype)
         all_ids = torch.empty(W * ids.numel(), dtype=ids.dtype, device=ids.device)
         all_rows = torch.empty((W * ids.numel(), width), dtype=rows.dtype, device=rows.device)
         dist.all_gather_into_tensor(all_ids, ids)
         dist.all_gather_into_tensor(all_rows, rows)
         table.index_fill_(0, ids, 0)
-        table.index_add_(0, all_ids, all_rows, alpha=1.0 / W)
+        table.index_add_(0, all_ids, all_rows.to(table.dtype), alpha=1.0 / W)
+        self.last_ids = all_ids                      # every row that carries gradient after the exchange
         self.done.append((lo, lo + n_rows * width))
 
     def finish(self):
@@ -147,12 +170,15 @@ class GradSync(object):
             for lo, hi in covered + [(self.flat.numel(), self.flat.numel())]:
                 if lo > pos:
                     for s in range(pos, lo, self.bucket):
-                        self.works.append(_avg_inplace(self.flat[s:min(s + self.bucket, lo)], async_op=True))
+                        self._submit(s, min(s + self.bucket, lo))
                 pos = max(pos, hi)
         for w in self.works:
             if w is not None:
                 w.wait()
-        self.works, self.done = [], []
+        for w, s, e in self.staged:
+            w.wait()
+            self.flat[s:e].copy_(self.comm[s:e])
+        self.works, self.done, self.staged = [], [], []
 
 
 # --------------------------------------------------------------------------------------------------

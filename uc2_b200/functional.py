@@ -68,6 +68,9 @@ def encoder_forward(enc, arena, input_ids, position_ids, img_feat, img_pos_feat,
             a.position_ids, a.position_rows = pos.data_ptr(), pos.size(0)
         elif not fam.derive_positions:
             raise ValueError("position_ids is required for the Uniter family")
+        lazy = getattr(arena, "lazy", None)
+        if lazy is not None:
+            lazy.catch_up(ids)              # deferred AdamW (optim.LazyRows): the rows about to be read become current
         a.word_emb = arena.mp(pre + "embeddings.word_embeddings.weight")
         a.pos_emb = arena.mp(pre + "embeddings.position_embeddings.weight")
         a.ln_w = arena.mp(pre + "embeddings.LayerNorm.weight")
@@ -202,6 +205,11 @@ def encoder_backward(enc, arena, st, dout):
             setattr(g, f, arena.gp(ip + n))
             names.append(ip + n)
     call("uc2_embed_pack_bwd", C.byref(st.args), dx0.data_ptr(), C.byref(g), stream())
+    if st.mode != 2:
+        # rows of the vocabulary table that now carry gradient, for the deferred AdamW (optim.LazyRows); a second
+        # backward pass into the same optimizer step makes the list incomplete -> None = treat the table as dense
+        arena.word_rows_n = getattr(arena, "word_rows_n", 0) + 1
+        arena.word_rows = st.keep[0] if arena.word_rows_n == 1 else None
     if st.mode != 1:
         ip = pre + "img_embeddings."
         dy_bf16 = torch.empty((B * R, 768), dtype=BF16, device=dout.device)
@@ -228,8 +236,11 @@ def encoder_backward(enc, arena, st, dout):
             w_end = arena.numel[wname]
             sync.sparse_rows_table(0, arena.shape[wname][0], arena.shape[wname][1], st.keep[0],
                                    pad_row=max(int(fam.word_pad), 0))
+            if arena.word_rows is not None:
+                arena.word_rows = sync.last_ids          # after the exchange: the rows of every rank
             sync.ready(w_end, q0_off)
         else:
+            arena.word_rows = None                       # dense all-reduce: any rank's rows may carry gradient now
             sync.ready(0, q0_off)                                                        # embeddings: last
 
 
@@ -259,6 +270,9 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, arena, wname, bname, act, transposed, out_f32):
+        lazy = getattr(arena, "lazy", None)
+        if lazy is not None and wname == lazy.name:
+            lazy.catch_up_all()             # the tied decoder reads every row of the vocabulary table
         Wm = arena.s(wname)
         n = x.size(0)
         N, K = (Wm.size(1), Wm.size(0)) if transposed else (Wm.size(0), Wm.size(1))
@@ -322,24 +336,36 @@ def _linear_backward(arena, wname, bname, x, dz, transposed, N, K):
 
 
 class LmHeadCEFn(torch.autograd.Function):
-    """Tied MLM decoder + cross entropy as one autograd node (model/layer.py:263-264 + model/model.py:592-596):
-    logits = h W_emb^T + bias (fp32, [n, 250 002]) -> per-row CE.  Backward writes d(logits) straight as the bf16 GEMM
-    operand (uc2_ce_loss_bwd_bf16), so the 0.6 GB fp32 d(logits) tensor and its cast never exist."""
+    """Tied MLM decoder + cross entropy as one autograd node (model/layer.py:263-264 + model/model.py:592-596).
+    Forward: ONE GEMM writes the logits h W_emb^T + bias as bf16 and, from the fp32 accumulators in its epilogue, a
+    (max, sum-exp) pair per row and 32-column chunk plus the label's logit (csrc/gemm_tcgen05.cu MODE 9);
+    uc2_ce_stats_reduce merges them into lse and the per-row loss.  No fp32 [n, 250 002] tensor exists.  Backward
+    turns the bf16 logits into d(logits) in place (uc2_ce_bwd_inplace_bf16), which is already the GEMM operand of the
+    decoder's dgrad / wgrad."""
 
     @staticmethod
     def forward(ctx, h, arena, wname, bname, targets, ignore_index):
+        lazy = getattr(arena, "lazy", None)
+        if lazy is not None and wname == lazy.name:
+            lazy.catch_up_all()             # the tied decoder reads every row of the table
         Wm = arena.s(wname)
         n, K = h.shape
         N = Wm.size(0)
         h = h.contiguous()
-        logits = torch.empty((n, _pad8(N)), dtype=F32, device=h.device)
-        loss = torch.empty((n,), dtype=F32, device=h.device)
-        lse = torch.empty((n,), dtype=F32, device=h.device)
+        dev = h.device
+        logits = torch.empty((n, _pad16(N)), dtype=BF16, device=dev)
+        loss = torch.empty((n,), dtype=F32, device=dev)
+        lse = torch.empty((n,), dtype=F32, device=dev)
         t = targets.to(torch.long).contiguous()
         if n:
-            _lib.gemm(h, Wm, n, N, K, bias=arena.m(bname), out_f32=logits[:, :N])
-            call("uc2_ce_loss_fwd", logits.data_ptr(), logits.stride(0), n, N, t.data_ptr(), ignore_index,
-                 loss.data_ptr(), lse.data_ptr(), stream())
+            n_chunks = (N + 31) // 32
+            stats = torch.empty((n_chunks, n, 2), dtype=F32, device=dev)
+            part = torch.empty(((n_chunks + 255) // 256, n, 2), dtype=F32, device=dev)
+            tgt = torch.zeros((n,), dtype=F32, device=dev)       # rows with an out-of-range (ignored) label keep 0
+            _lib.gemm(h, Wm, n, N, K, bias=arena.m(bname), out_bf16=logits[:, :N], ld_out=logits.stride(0),
+                      ce=(stats, t, tgt))
+            call("uc2_ce_stats_reduce", stats.data_ptr(), n, n_chunks, n, tgt.data_ptr(), t.data_ptr(), ignore_index,
+                 part.data_ptr(), loss.data_ptr(), lse.data_ptr(), stream())
         ctx.save_for_backward(h, logits, lse, t)
         ctx.meta = (arena, wname, bname, N, K, ignore_index)
         return loss
@@ -352,10 +378,14 @@ class LmHeadCEFn(torch.autograd.Function):
         if n == 0:
             return torch.zeros_like(h), None, None, None, None, None
         dloss = dloss.to(F32).contiguous()
-        dz = torch.empty((n, logits.stride(0)), dtype=BF16, device=h.device)
-        call("uc2_ce_loss_bwd_bf16", logits.data_ptr(), logits.stride(0), n, N, t.data_ptr(), ignore_index,
-             dloss.data_ptr(), lse.data_ptr(), dz.data_ptr(), dz.stride(0), stream())
-        return _linear_backward(arena, wname, bname, h, dz[:, :N], False, N, K), None, None, None, None, None
+        # in place: the saved logits become d(logits) (this node's backward runs once)
+        call("uc2_ce_bwd_inplace_bf16", logits.data_ptr(), logits.stride(0), n, N, t.data_ptr(), ignore_index,
+             dloss.data_ptr(), lse.data_ptr(), stream())
+        return _linear_backward(arena, wname, bname, h, logits[:, :N], False, N, K), None, None, None, None, None
+
+
+def _pad16(n):
+    return (n + 15) // 16 * 16
 
 
 def _pad8(n):

@@ -190,6 +190,15 @@ class UC2PreTrainedModel(nn.Module):
         if isinstance(module, nn.Linear) and module.bias is not None:
             module.bias.data.zero_()
 
+    def state_dict(self, *args, **kwargs):
+        """The reference's nn.Module.state_dict(); with a deferred optimizer (optim.AdamW(lazy_rows=True)) the postponed
+        word-embedding row updates are applied first, so the tensors handed out are what eager AdamW would hold."""
+        a = object.__getattribute__(_root_of(self), "_uc2_arena_obj") if hasattr(_root_of(self), "_uc2_arena_obj") else None
+        lazy = getattr(a, "lazy", None) if a is not None else None
+        if lazy is not None:
+            lazy.catch_up_all()
+        return super().state_dict(*args, **kwargs)
+
     # ---- arena ----------------------------------------------------------------------------------
     def _arena(self):
         root = _root_of(self)

@@ -30,7 +30,12 @@ class AdamW(object):
     ``clip_grad_norm_(optimizer, max_norm)`` below and fused into the same launch; zero_grad() is fused too.
     """
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True,
+                 lazy_rows=False):
+        """lazy_rows: postpone the update of word-embedding rows that have no gradient in a step until the row is
+        needed (include/uc2_b200.h, uc2_lazy_table).  Parameters and moments end up bit-identical to the eager update;
+        every forward pass sees current rows.  Whoever reads the raw parameter tensor or the optimizer state calls
+        flush() first (state_dict() of the optimizer and of the models do)."""
         if lr < 0.0:
             raise ValueError("Invalid learning rate: {} - should be >= 0.0".format(lr))
         if not 0.0 <= betas[0] < 1.0:
@@ -58,6 +63,9 @@ class AdamW(object):
         self._pending_clip = 0.0
         self._fused_zero = True
         self.state = {}
+        self.lazy_rows = bool(lazy_rows)
+        self.lazy_ok = True            # the trainer clears it when several backward passes feed one step
+        self._lazy = None              # LazyRows once bound
 
     # ---------------------------------------------------------------------------------------------
     def _bind(self):
@@ -93,6 +101,14 @@ class AdamW(object):
         self.exp_avg = torch.zeros_like(arena.master)
         self.exp_avg_sq = torch.zeros_like(arena.master)
         self._sqnorm = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._lazy = None
+        arena.lazy = None
+        if self.lazy_rows:
+            tables = [n for n in arena.names if n.endswith("embeddings.word_embeddings.weight") and
+                      len(arena.shape[n]) == 2 and arena.shape[n][1] % 4 == 0 and group_of[arena.index[n]] >= 0]
+            if tables:
+                self._lazy = LazyRows(self, arena, tables[0])
+                arena.lazy = self._lazy
 
     def _refresh_active(self, step):
         a = self._arena
@@ -105,13 +121,29 @@ class AdamW(object):
         if changed:
             self._act.copy_(torch.tensor(self._act_host, dtype=torch.int32), non_blocking=False)
 
+    def _sparse_step(self):
+        """Row ids of the word-embedding gradient when this step can take the deferred path, else None."""
+        lz = self._lazy
+        if lz is None or not self.lazy_ok:
+            return None
+        a = self._arena
+        if getattr(a, "word_emb_dense", False) or self._act_host[lz.tensor] < 0:
+            return None
+        if getattr(a, "word_rows_n", 0) != 1:        # no / several embedding backward passes: no complete row list
+            return None
+        return getattr(a, "word_rows", None)
+
     def grad_norm(self):
         """Global L2 norm of the gradients of every tensor that has one (device tensor, no host sync)."""
         self._bind()
         self._refresh_active(self.global_step + 1)
         a = self._arena
-        call("uc2_grad_sqnorm", a.grad.data_ptr(), self._chunks.data_ptr(), self._n_chunks, self._act.data_ptr(),
+        rows = self._sparse_step()
+        act = self._act if rows is None else self._lazy.act_without_table()
+        call("uc2_grad_sqnorm", a.grad.data_ptr(), self._chunks.data_ptr(), self._n_chunks, act.data_ptr(),
              self._sqnorm.data_ptr(), stream())
+        if rows is not None:
+            self._lazy.add_sqnorm(rows, self._sqnorm)
         return self._sqnorm.sqrt().float()
 
     def step(self, closure=None):
@@ -131,13 +163,33 @@ class AdamW(object):
         h.correct_bias, h.global_step = int(g0["correct_bias"]), self.global_step
         h.max_grad_norm = float(self._pending_clip)
         h.zero_grad = int(self._fused_zero)
+        sq = self._sqnorm.data_ptr() if self._pending_clip > 0 else None
+        lz = self._lazy
+        rows = self._sparse_step()
+        act = self._act
+        if lz is not None:
+            if rows is None:
+                lz.catch_up_all()                    # eager step on the table: every row has to be current first
+            else:
+                act = lz.act_without_table()
         call("uc2_adamw_step", a.master.data_ptr(), a.grad.data_ptr(), self.exp_avg.data_ptr(),
              self.exp_avg_sq.data_ptr(), a.shadow.data_ptr(), self._chunks.data_ptr(), self._n_chunks,
-             self._act.data_ptr(), self._group_of.data_ptr(), C.byref(h),
-             self._sqnorm.data_ptr() if self._pending_clip > 0 else None, stream())
+             act.data_ptr(), self._group_of.data_ptr(), C.byref(h), sq, stream())
+        if lz is not None:
+            if rows is None:
+                lz.mark_all(self.global_step)
+            else:
+                lz.step_rows(rows, self.global_step, h, sq)
+        a.word_rows, a.word_rows_n = None, 0
         self._pending_clip = 0.0
         a.mark_synced()
         return loss
+
+    def flush(self):
+        """Apply every postponed row update (no-op without lazy_rows): afterwards the parameter tensors and the
+        optimizer state are what eager AdamW would hold."""
+        if self._lazy is not None:
+            self._lazy.catch_up_all()
 
     def zero_grad(self, set_to_none=False):
         """Gradients were already cleared inside step() (fused); tensors that never had a gradient are zero."""
@@ -153,6 +205,7 @@ class AdamW(object):
         return [p for g in self.param_groups for p in g["params"]]
 
     def state_dict(self):
+        self.flush()
         groups, k = [], 0
         for g in self.param_groups:
             d = {key: v for key, v in g.items() if key != "params"}
@@ -202,6 +255,86 @@ class AdamW(object):
             self._act_host[a.index[n]] = self.global_step - int(st["step"]) + 1
             a.active[n] = True
         self._act.copy_(torch.tensor(self._act_host, dtype=torch.int32))
+        if self._lazy is not None:
+            self._lazy.reset(self.global_step)
+
+
+class LazyRows(object):
+    """Host side of the deferred word-embedding update (include/uc2_b200.h uc2_lazy_table; csrc/optim.cu)."""
+    HIST = 4096
+
+    def __init__(self, opt, arena, name):
+        self.opt, self.arena, self.name = opt, arena, name
+        dev = arena.master.device
+        self.tensor = arena.index[name]
+        self.n_rows, self.width = arena.shape[name]
+        self.row_step = torch.full((self.n_rows,), opt.global_step, dtype=torch.int32, device=dev)
+        self.row_seen = torch.full((self.n_rows,), -1, dtype=torch.int32, device=dev)
+        self.hist = torch.zeros((self.HIST, 2), dtype=torch.float32, device=dev)
+        self.pending = False                 # some row may be behind
+        self.last_full = opt.global_step     # last step at which every row was current
+        self._mark = 0
+        self._act_nt = None
+        self._act_nt_src = None
+        g = opt.param_groups[opt._group_of_host[self.tensor]]
+        self.group = opt._group_of_host[self.tensor]
+        t = _lib.LazyTable()
+        t.param, t.grad = arena.master.data_ptr(), arena.grad.data_ptr()
+        t.exp_avg, t.exp_avg_sq = opt.exp_avg.data_ptr(), opt.exp_avg_sq.data_ptr()
+        t.table_off, t.n_rows, t.width = arena.offset[name], self.n_rows, self.width
+        t.row_step, t.row_seen = self.row_step.data_ptr(), self.row_seen.data_ptr()
+        t.hist, t.hist_len = self.hist.data_ptr(), self.HIST
+        t.beta1, t.beta2, t.eps = g["betas"][0], g["betas"][1], g["eps"]
+        t.decay_on = int(g["weight_decay"] > 0)
+        t.shadow_bf16 = arena.shadow.data_ptr()
+        self.table = t
+
+    def reset(self, step):
+        self.row_step.fill_(step)
+        self.pending, self.last_full = False, step
+
+    def act_without_table(self):
+        """The optimizer's first-active-step vector with the table switched off (the eager kernel skips it)."""
+        if self._act_nt is None or self._act_nt_src != self.opt._act_host:
+            host = list(self.opt._act_host)
+            host[self.tensor] = -1
+            self._act_nt = torch.tensor(host, dtype=torch.int32).to(self.opt._act.device)
+            self._act_nt_src = list(self.opt._act_host)
+        return self._act_nt
+
+    def _ids(self, rows):
+        return rows.reshape(-1).to(torch.long).contiguous()
+
+    def add_sqnorm(self, rows, out):
+        ids = self._ids(rows)
+        self._mark += 1
+        call("uc2_grad_sqnorm_rows", C.byref(self.table), ids.data_ptr(), ids.numel(), self._mark, out.data_ptr(), stream())
+
+    def step_rows(self, rows, step, h, sqnorm_ptr):
+        g = self.opt.param_groups[self.group]
+        first = self.opt._act_host[self.tensor]
+        ids = self._ids(rows)
+        call("uc2_adamw_lazy_rows", C.byref(self.table), ids.data_ptr(), ids.numel(), step, first, g["lr"],
+             g["weight_decay"], int(g["correct_bias"]), float(h.max_grad_norm), sqnorm_ptr, stream())
+        self.pending = True
+        if step - self.last_full >= self.HIST - 2:      # the ring is about to wrap over a step some row still needs
+            self.catch_up_all()
+
+    def catch_up(self, rows):
+        """Before a forward pass reads these rows of the fp32 table."""
+        if self.pending and self.opt.global_step > self.last_full:
+            ids = self._ids(rows)
+            call("uc2_adamw_lazy_catchup", C.byref(self.table), ids.data_ptr(), ids.numel(), self.opt.global_step, stream())
+
+    def catch_up_all(self):
+        """Before anything reads the whole table (the tied MLM decoder, checkpoints, an eager step on the table)."""
+        if self.pending and self.opt.global_step > self.last_full:
+            call("uc2_adamw_lazy_catchup", C.byref(self.table), None, 0, self.opt.global_step, stream())
+        self.pending, self.last_full = False, self.opt.global_step
+
+    def mark_all(self, step):
+        self.row_step.fill_(step)
+        self.pending, self.last_full = False, step
 
 
 def clip_grad_norm_(optimizer, max_norm):

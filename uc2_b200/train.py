@@ -35,7 +35,7 @@ def reduce_loss(out, task, itm_ot_lambda=0.1, ot_pos_only=False):
 
 class TrainStep(object):
     def __init__(self, model, optimizer, grad_norm=-1.0, gradient_accumulation_steps=1, itm_ot_lambda=0.1,
-                 lr_fn=None, bucket_bytes=64 << 20, layers_per_segment=3):
+                 lr_fn=None, bucket_bytes=64 << 20, layers_per_segment=3, grad_comm_dtype=None):
         self.model, self.optimizer = model, optimizer
         self.grad_norm = grad_norm
         self.accum = gradient_accumulation_steps
@@ -45,6 +45,7 @@ class TrainStep(object):
         self.global_step = 0
         self.bucket_bytes = bucket_bytes
         self.layers_per_segment = layers_per_segment
+        self.grad_comm_dtype = grad_comm_dtype      # e.g. torch.bfloat16: 2 bytes per gradient on the wire, as the reference
         self.sync = None
         self.last_out = None              # raw model output of the last micro-step (for loop bookkeeping)
         self.last_grad_norm = None        # device scalar: total gradient norm before clipping, last optimizer step
@@ -52,7 +53,7 @@ class TrainStep(object):
     def _ensure_sync(self):
         arena = self.model._arena()
         if D.size() > 1 and (self.sync is None or self.sync.flat.data_ptr() != arena.grad.data_ptr()):
-            self.sync = D.GradSync(arena.grad, self.bucket_bytes)
+            self.sync = D.GradSync(arena.grad, self.bucket_bytes, comm_dtype=self.grad_comm_dtype)
             self.sync.layers_per_segment = self.layers_per_segment
             self.sync.allow_sparse = self.accum == 1     # with accumulation earlier micro-steps touched other rows
             arena.grad_sync = self.sync
@@ -61,6 +62,8 @@ class TrainStep(object):
     def __call__(self, batch, task=None):
         """One micro-step; runs the optimizer when the accumulation window closes.  Returns the (device) loss."""
         self._ensure_sync()
+        if hasattr(self.optimizer, "lazy_ok"):
+            self.optimizer.lazy_ok = self.accum == 1      # several backward passes per step: no complete row list
         last = (self.micro + 1) % self.accum == 0
         if self.sync is not None:
             self.sync.enabled = last               # only the last micro-step's backward triggers communication
