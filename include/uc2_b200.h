@@ -412,7 +412,9 @@ UC2_API int uc2_adamw_lazy_note(const uc2_lazy_table* t, int step, int first_ste
 /* Bring rows up to date through step `upto` (row_ids == NULL: every row). */
 UC2_API int uc2_adamw_lazy_catchup(const uc2_lazy_table* t, const long long* row_ids, long long n_ids, int upto,
                                    void* stream);
-/* *out += sum of squares of the gradient rows in row_ids, every distinct row once (mark = a value no earlier call used) */
+/* *out += the table's share of the squared gradient norm on a row-sparse step: the eager kernel's per-chunk partial
+ * sums (8192-element slices counted from table_off) of exactly those chunks that hold a row of row_ids, each distinct
+ * chunk once (mark = a value no earlier call used; row_seen is the scratch) -- every other chunk of the table is zero. */
 UC2_API int uc2_grad_sqnorm_rows(const uc2_lazy_table* t, const long long* row_ids, long long n_ids, int mark,
                                  double* out, void* stream);
 

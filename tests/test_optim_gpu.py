@@ -231,3 +231,79 @@ def test_pretrain_loop_end_to_end(tmp_path):
     assert any(n.startswith("valid_itm_coco/itm_coco_valid/") for n in names)
     assert any("examples trained" in l for l in lines)
     assert m.training
+
+
+def test_deferred_embedding_rows_are_bit_exact():
+    """AdamW(lazy_rows=True) postpones the update of vocabulary rows without gradient and replays it when the row is
+    needed (csrc/optim.cu, uc2_lazy_table).  Two copies of a model, one eager and one deferred, are fed IDENTICAL
+    gradients for nine steps over changing batches and tasks (an MLM step in the middle makes the table dense): every
+    forward loss is bit-equal along the way (a forward always sees current rows), rows really are behind in between,
+    and after flush() parameters and both moments are bit-identical."""
+    from uc2_b200 import model
+    from uc2_b200.batch import to_device
+    from uc2_b200.optim import AdamW, clip_grad_norm_
+    from uc2_b200.train import reduce_loss
+    from uc2_b200.utils import set_dropout
+    from oracle import uc2_oracle as O
+    cfg = cases.config(2)
+    sd = cases.weights(cfg, "pretrain")
+
+    def make(lazy):
+        m = model.VLXLMRForPretraining(cfg, 2048, 1601)
+        m.load_state_dict(cases.with_aliases(sd, "pretrain"), strict=False)
+        m.cuda().train()
+        set_dropout(m, 0)
+        decay = [p for n, p in m.named_parameters() if not O.no_decay(n)]
+        nodecay = [p for n, p in m.named_parameters() if O.no_decay(n)]
+        opt = AdamW([{"params": decay, "weight_decay": 0.01}, {"params": nodecay, "weight_decay": 0.0}], lr=3e-4,
+                    betas=(0.9, 0.98), lazy_rows=lazy)
+        return m, opt
+
+    ma, oa = make(False)
+    mb, ob = make(True)
+    plan = [("mrfr", cases.batch_mrfr(seed=41)), ("itm", cases.batch_itm(seed=42)), ("mrfr", cases.batch_mrfr(seed=43)),
+            ("mlm", cases.batch_mlm(seed=44)), ("itm", cases.batch_itm(seed=45)), ("mrc-kl", cases.batch_mrc(seed=46)),
+            ("itm", cases.batch_itm(seed=42)), ("mrfr", cases.batch_mrfr(seed=47)), ("itm", cases.batch_itm(seed=48))]
+    wname = "roberta.embeddings.word_embeddings.weight"
+    behind = 0
+    for s, (task, b) in enumerate(plan, 1):
+        bd = to_device(b, "cuda")
+        la = reduce_loss(ma(bd, task=task, compute_loss=True), task)
+        lb = reduce_loss(mb(bd, task=task, compute_loss=True), task)
+        assert la.item() == lb.item(), (s, task, la.item(), lb.item())       # same weights where it matters
+        la.backward()
+        lb.backward()
+        aa, ab = ma._arena(), mb._arena()
+        ab.grad.copy_(aa.grad)             # identical gradients (the backward's fp32 atomics are not run-to-run exact)
+        for o in (oa, ob):
+            o.lr_now = 3e-4 * (1.0 - 0.05 * s)
+            for g in o.param_groups:
+                g["lr"] = o.lr_now         # a changing learning rate: the replay has to use each step's own
+            clip_grad_norm_(o, 1.0)
+            o.step()
+            o.zero_grad()
+        torch.cuda.synchronize()
+        assert ob._lazy is not None
+        if not torch.equal(aa.m(wname), ab.m(wname)):
+            behind += 1
+    assert behind >= 4, "the deferred path never left a row behind: it is not being exercised"
+    ob.flush()
+    torch.cuda.synchronize()
+    aa, ab = ma._arena(), mb._arena()
+    as_bits = lambda t: t.view(torch.int32)
+    for what, x, y in (("master", aa.master, ab.master), ("exp_avg", oa.exp_avg, ob.exp_avg),
+                       ("exp_avg_sq", oa.exp_avg_sq, ob.exp_avg_sq)):
+        bad = (as_bits(x) != as_bits(y)).nonzero().reshape(-1)
+        if bad.numel():
+            o = aa.offset[wname]
+            in_table = int(((bad >= o) & (bad < o + aa.numel[wname])).sum())
+            i = int(bad[0])
+            print(f"{what}: {bad.numel()} of {x.numel()} elements differ ({in_table} inside the word table); first at {i}: "
+                  f"{x[i].item()!r} vs {y[i].item()!r}; table row {(i - o) // 768 if o <= i < o + aa.numel[wname] else None}")
+    assert torch.equal(as_bits(aa.master), as_bits(ab.master))
+    assert torch.equal(as_bits(oa.exp_avg), as_bits(ob.exp_avg))
+    assert torch.equal(as_bits(oa.exp_avg_sq), as_bits(ob.exp_avg_sq))
+    assert torch.equal(aa.shadow.view(torch.int16), ab.shadow.view(torch.int16))
+    # and the checkpoint view flushes by itself
+    sa, sb = ma.state_dict(), mb.state_dict()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)

@@ -23,32 +23,43 @@ cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long
     }
 }
 
-// sum of squares of the gradients of ACTIVE tensors (act_step >= 0) into *out (double)
-__global__ void __launch_bounds__(OPT_THREADS)
-grad_sqnorm_kernel(const float* __restrict__ grad, const uc2_opt_chunk* __restrict__ chunks, int n_chunks,
-                   const int* __restrict__ act_step, double* __restrict__ out) {
-    __shared__ float red[OPT_THREADS / 32];
+// This thread's share of the sum of squares of one <= CHUNK-element gradient slice (fixed order and rounding: the
+// eager and the row-sparse norm kernels must produce the same per-chunk partial sums)
+__device__ __forceinline__ float chunk_sqsum(const float* __restrict__ g, int n) {
     float acc = 0.f;
-    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const uc2_opt_chunk ch = chunks[c];
-        if (act_step[ch.tensor] < 0) continue;
-        const float* g = grad + ch.offset;
-        for (int i = threadIdx.x * 4; i < ch.n; i += OPT_THREADS * 4) {
-            if (i + 4 <= ch.n) {
-                const float4 v = *reinterpret_cast<const float4*>(g + i);
-                acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-            } else {
-                for (int k = i; k < ch.n; ++k) acc += g[k] * g[k];
-            }
+    for (int i = threadIdx.x * 4; i < n; i += OPT_THREADS * 4) {
+        if (i + 4 <= n) {
+            const float4 v = *reinterpret_cast<const float4*>(g + i);
+            acc = __fadd_rn(acc, __fmaf_rn(v.w, v.w, __fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, __fmul_rn(v.x, v.x)))));
+        } else {
+            for (int k = i; k < n; ++k) acc = __fmaf_rn(g[k], g[k], acc);
         }
     }
+    return acc;
+}
+
+// block-wide sum of the per-thread shares of ONE chunk, added to *out in double (an all-zero chunk adds nothing)
+__device__ __forceinline__ void chunk_sqsum_commit(float acc, float* red, double* out) {
     acc = warp_sum(acc);
+    __syncthreads();                                 // red[] of the previous chunk has been consumed
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < OPT_THREADS / 32; ++w) s += red[w];
-        atomicAdd(out, s);
+        if (s != 0.0) atomicAdd(out, s);
+    }
+}
+
+// sum of squares of the gradients of ACTIVE tensors (act_step >= 0) into *out (double), one partial per chunk
+__global__ void __launch_bounds__(OPT_THREADS)
+grad_sqnorm_kernel(const float* __restrict__ grad, const uc2_opt_chunk* __restrict__ chunks, int n_chunks,
+                   const int* __restrict__ act_step, double* __restrict__ out) {
+    __shared__ float red[OPT_THREADS / 32];
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const uc2_opt_chunk ch = chunks[c];
+        if (act_step[ch.tensor] < 0) continue;
+        chunk_sqsum_commit(chunk_sqsum(grad + ch.offset, ch.n), red, out);
     }
 }
 
@@ -56,11 +67,12 @@ grad_sqnorm_kernel(const float* __restrict__ grad, const uc2_opt_chunk* __restri
 // the deferred kernels: the deferred replay has to reproduce the eager result bit for bit.
 __device__ __forceinline__ void adamw_update(float& p, float& m, float& v, float g, float beta1, float beta2, float eps,
                                              float step_size, float decay, bool decay_on) {
-    m = m * beta1 + (1.0f - beta1) * g;
-    v = v * beta2 + (1.0f - beta2) * g * g;
-    const float denom = sqrtf(v) + eps;
-    p = p - step_size * (m / denom);
-    if (decay_on) p = p - decay * p;
+    // every rounding spelled out: the compiler must not contract these differently in different kernels
+    m = __fmaf_rn(1.0f - beta1, g, __fmul_rn(m, beta1));
+    v = __fmaf_rn(__fmul_rn(1.0f - beta2, g), g, __fmul_rn(v, beta2));
+    const float denom = __fadd_rn(__fsqrt_rn(v), eps);
+    p = __fmaf_rn(-step_size, __fdiv_rn(m, denom), p);
+    if (decay_on) p = __fmaf_rn(-decay, p, p);
 }
 
 // step size of tensor-step `step` with the bias correction folded in (adamw.py:87-92)
@@ -201,31 +213,23 @@ __global__ void adamw_lazy_note_kernel(const uc2_lazy_table t, int step, int ten
     }
 }
 
-// sum of squares of the listed gradient rows, every distinct row once
+// Norm contribution of the table on a row-sparse step: the chunks (the eager kernel's CHUNK-element slices of the table)
+// that hold a listed row, every distinct chunk once, with the eager kernel's own per-chunk arithmetic; every other
+// chunk of the table is all zero and would add nothing.  Two CTAs per id: the chunk of the row's first / last element.
 __global__ void __launch_bounds__(OPT_THREADS)
-grad_sqnorm_rows_kernel(const uc2_lazy_table t, const long long* __restrict__ row_ids, long long n_ids, int mark,
-                        double* __restrict__ out) {
+grad_sqnorm_rows_kernel(const uc2_lazy_table t, const long long* __restrict__ row_ids, int mark, double* __restrict__ out) {
     __shared__ float red[OPT_THREADS / 32];
     __shared__ int s_old;
-    const long long r = row_ids[blockIdx.x];
+    const long long r = row_ids[blockIdx.x >> 1];
     if (r < 0 || r >= t.n_rows) return;
-    if (threadIdx.x == 0) s_old = atomicExch(t.row_seen + r, mark);
+    const long long total = (long long)t.n_rows * t.width;
+    const long long c = (r * t.width + ((blockIdx.x & 1) ? t.width - 1 : 0)) / CHUNK;
+    if (threadIdx.x == 0) s_old = atomicExch(t.row_seen + c, mark);
     __syncthreads();
     if (s_old == mark) return;
-    const float* g = t.grad + t.table_off + r * t.width;
-    float acc = 0.f;
-    for (int i = threadIdx.x * 4; i < t.width; i += OPT_THREADS * 4) {
-        const float4 v = *reinterpret_cast<const float4*>(g + i);
-        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int w = 0; w < OPT_THREADS / 32; ++w) s += red[w];
-        atomicAdd(out, s);
-    }
+    const long long start = c * CHUNK;
+    const int n = (int)(total - start < CHUNK ? total - start : CHUNK);
+    chunk_sqsum_commit(chunk_sqsum(t.grad + t.table_off + start, n), red, out);
 }
 
 int lazy_check(const uc2_lazy_table* t, const char* who) {
@@ -280,7 +284,7 @@ extern "C" UC2_API int uc2_grad_sqnorm_rows(const uc2_lazy_table* t, const long 
     if (int rc = lazy_check(t, "grad_sqnorm_rows")) return rc;
     UC2_REQUIRE(out && (row_ids || n_ids == 0), UC2_ERR_ARG, "grad_sqnorm_rows: bad args");
     if (n_ids <= 0) return UC2_OK;
-    grad_sqnorm_rows_kernel<<<(unsigned)n_ids, OPT_THREADS, 0, (cudaStream_t)stream>>>(*t, row_ids, n_ids, mark, out);
+    grad_sqnorm_rows_kernel<<<(unsigned)(2 * n_ids), OPT_THREADS, 0, (cudaStream_t)stream>>>(*t, row_ids, mark, out);
     return check_last("grad_sqnorm_rows_kernel");
 }
 

@@ -181,6 +181,7 @@ class AdamW(object):
             else:
                 lz.step_rows(rows, self.global_step, h, sq)
         a.word_rows, a.word_rows_n = None, 0
+        a.word_emb_dense = False             # these three describe the gradient accumulated for ONE optimizer step
         self._pending_clip = 0.0
         a.mark_synced()
         return loss
@@ -355,7 +356,9 @@ def build_optimizer(model, opts):
         {"params": [p for n, p in param_optimizer if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
     if opts.optim != "adamw":
         raise ValueError("invalid optimizer (the B200 path implements adamw, the optimiser both shipped configs use)")
-    return AdamW(optimizer_grouped_parameters, lr=opts.learning_rate, betas=opts.betas)
+    # deferred row updates for the word-embedding table (bit-identical to the eager update) unless switched off
+    return AdamW(optimizer_grouped_parameters, lr=opts.learning_rate, betas=opts.betas,
+                 lazy_rows=bool(getattr(opts, "lazy_embedding_rows", True)))
 
 
 # ---- optim/sched.py -----------------------------------------------------------------------------------

@@ -75,7 +75,6 @@ class TrainStep(object):
         if last:
             if self.sync is not None:
                 self.sync.finish()
-            self.model._arena().word_emb_dense = False
             self.global_step += 1
             if self.lr_fn is not None:
                 lr = self.lr_fn(self.global_step)              # one value, or one per parameter group
@@ -86,4 +85,5 @@ class TrainStep(object):
                 self.last_grad_norm = clip_grad_norm_(self.optimizer, self.grad_norm)
             self.optimizer.step()
             self.optimizer.zero_grad()
+            self.model._arena().word_emb_dense = False      # describes the gradient of ONE optimizer step
         return loss.detach()
