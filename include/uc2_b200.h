@@ -204,24 +204,32 @@ UC2_API int uc2_attention_bwd(const void* qkv, const long long* attn_mask, const
                               const float* lse, float* delta_ws, void* dqkv, int B, int S, void* stream);
 
 /* Training forms with attention-probability dropout (model/layer.py:94): P is dropped and rescaled after the
- * softmax normalisation; element (q, k) of (batch b, head h) is kept iff
- * (lowbias32((q * S + k) ^ drop_head_key(drop_key, b * 12 + h)) >> 16) >= drop_thresh.  S <= 256. */
+ * softmax normalisation (the normaliser keeps every key).  Forward and backward regenerate the mask from
+ * (drop_key, batch * 12 + head, query, key); drop_thresh = round(p * 65536) < 65536, drop_scale = 1 / (1 - p),
+ * drop_thresh = 0 switches it off.  S <= 256.
+ *
+ * Which kernels run: by default the tcgen05 / TMEM kernels below for every shape they take (forward S <= 256,
+ * backward S <= 160), the mma.sync kernels of csrc/attention.cu otherwise.  The two families draw the dropout mask
+ * from different counter streams (tcgen05: one lowbias32 per 16 x 16 block of the [S, S] mask, then
+ * e = h * CA^(q & 15) * CB^(k & 15) mod 2^32, kept iff e >= drop_thresh << 16 -- uc2_b200/dropout.py
+ * attn_keep_mask_np is the host mirror; mma.sync: keep_mask_np over q * S + k), so with dropout on the forward only
+ * goes to tcgen05 when the backward of that shape does too. */
 UC2_API int uc2_attention_fwd_dropout(const void* qkv, const long long* attn_mask, void* ctx, float* lse, int B, int S,
                                       unsigned int drop_key, unsigned int drop_thresh, float drop_scale, void* stream);
 UC2_API int uc2_attention_bwd_dropout(const void* qkv, const long long* attn_mask, const void* ctx, const void* dctx,
                                       const float* lse, float* delta_ws, void* dqkv, int B, int S,
                                       unsigned int drop_key, unsigned int drop_thresh, float drop_scale, void* stream);
-/* EXPERIMENTAL (not yet run on hardware, off by default): the same forward with both products on tcgen05 tensor
- * cores and accumulators in TMEM, S <= 160 (UC2_ERR_UNSUPPORTED above).  Same arguments and, by construction, the
- * same results (mask, dropout stream, lse) as uc2_attention_fwd_dropout, so uc2_attention_bwd* pairs with it; ctx
- * must be 32-byte aligned.  uc2_attention_tc_enable(1) (or UC2_ATTN_TCGEN05=1 in the environment) makes
- * the public entry points (uc2_attention_fwd*, _bwd*, uc2_encoder_fwd*, _bwd*) route eligible shapes to the _tc
- * kernels; it returns the previous setting. */
+/* The tcgen05 / TMEM attention kernels themselves (csrc/attention_tc.cu), same arguments and outputs: S = Q K^T and
+ * O = P V on the 5th-generation tensor cores with the accumulators (and P, as the TMEM-A operand of P V) in tensor
+ * memory, Q / K / V tiles by TMA.  Forward: S <= 256, ctx 32-byte aligned.  Backward: S <= 160, dqkv 32-byte aligned
+ * and fully overwritten for the B*S rows; delta = rowsum(dO * O) is computed inside from the dO and O tiles, so there
+ * is no workspace argument.  UC2_ERR_UNSUPPORTED above those lengths.  A mask row that is a prefix of ones (every
+ * UC2 collate) only costs its valid keys: masked keys have probability exactly 0 in fp32 next to any valid key.
+ * uc2_attention_tc_enable(0) (or UC2_ATTN_TCGEN05=0 in the environment) routes the public entry points
+ * (uc2_attention_fwd*, _bwd*, uc2_encoder_fwd*, _bwd*) back to the mma.sync kernels; it returns the previous setting.
+ * UC2_ATTN_TC_BWD_SPLIT=2 runs the backward with 8 instead of 16 element-wise warps (a tuning knob; same results). */
 UC2_API int uc2_attention_fwd_tc(const void* qkv, const long long* attn_mask, void* ctx, float* lse, int B, int S,
                                  unsigned int drop_key, unsigned int drop_thresh, float drop_scale, void* stream);
-/* ... and the backward (dqkv fully overwritten for the B*S rows; delta = rowsum(dO * O) is computed inside, so
- * there is no workspace argument).  dqkv must be 32-byte aligned.  UC2_ATTN_TC_BWD_SPLIT=4 in the environment runs
- * it with 16 instead of 8 element-wise warps (a tuning knob; same results). */
 UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* attn_mask, const void* ctx, const void* dctx,
                                  const float* lse, void* dqkv, int B, int S, unsigned int drop_key,
                                  unsigned int drop_thresh, float drop_scale, void* stream);

@@ -23,7 +23,7 @@ def _tc(on):
 
 SHAPES = [(6, 160, "prefix"), (3, 76, "prefix"), (2, 128, "random"), (5, 33, "random"), (2, 16, "prefix"),
           (3, 150, "prefix"), (4, 129, "random"), (150, 160, "prefix")]
-# the forward also serves packed lengths up to 256 (BASELINE configs[4], VTLM: S = 222)
+# packed lengths up to 256 (BASELINE configs[4], VTLM: S = 222): one CTA per SM in the forward, two query blocks in the backward
 FWD_SHAPES = SHAPES + [(3, 161, "random"), (4, 222, "prefix"), (2, 192, "random"), (3, 256, "prefix"), (40, 222, "prefix")]
 
 
@@ -159,7 +159,7 @@ def _run_bwd_raw(name, qkv, mask, ctx, dctx, lse, B, S, drop):
     return dqkv
 
 
-@pytest.mark.parametrize("B,S,kind", SHAPES)
+@pytest.mark.parametrize("B,S,kind", FWD_SHAPES)
 def test_tc_backward_matches_reference_and_mma_sync(B, S, kind):
     qkv, mask = _inputs(B, S, kind)
     dctx = torch.randn(B * S, 768, device="cuda").bfloat16()
@@ -173,7 +173,8 @@ def test_tc_backward_matches_reference_and_mma_sync(B, S, kind):
     assert (dqkv.float() - d0.float()).abs().max().item() <= 1.5e-2 * scale
 
 
-@pytest.mark.parametrize("B,S,kind", [(6, 160, "prefix"), (3, 77, "random"), (4, 150, "prefix"), (5, 33, "prefix")])
+@pytest.mark.parametrize("B,S,kind", [(6, 160, "prefix"), (3, 77, "random"), (4, 150, "prefix"), (5, 33, "prefix"),
+                                      (3, 222, "prefix"), (2, 256, "random"), (2, 176, "random")])
 def test_tc_backward_dropout_matches_reference_with_host_mirror_mask(B, S, kind):
     """Forward and backward regenerate the same attention-dropout mask: torch autograd through the dropped
     probabilities (mask from the host mirror) gives the gradients the kernel must produce."""

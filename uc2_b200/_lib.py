@@ -195,9 +195,7 @@ def attention_kernels(S):
     """Which attention kernels the public entry points run for a packed length S (for the bench line)."""
     if not attention_tc_enabled() or S > 256:
         return "mma.sync (attention.cu)"
-    if S <= 160:
-        return "tcgen05/TMEM forward + backward (attention_tc.cu)"
-    return "tcgen05/TMEM forward when attention dropout is off, else mma.sync; mma.sync backward"
+    return "tcgen05/TMEM forward + backward (attention_tc.cu)"
 
 
 def launch_count():

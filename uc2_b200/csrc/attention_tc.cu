@@ -1,28 +1,11 @@
-// tcgen05 / TMEM forward attention for S <= 160 (every BASELINE training shape but VTLM), 12 heads x 64.
-// Replaces the same reference code as attention.cu (BertSelfAttention.forward model/layer.py:80-100) with the
-// two products on the 5th-generation tensor cores instead of mma.sync:
-//
-//   persistent CTAs (one per SM) loop over (batch, head) items; per item
-//     warp 0      TMA producer: Q, K, V of the head as three [SP x 64] SWIZZLE_128B boxes of the packed qkv
-//                 tensor (double buffered: the next item's tiles land under this item's softmax), and the
-//                 additive key-mask row in the exp2 domain
-//     warp 1      one thread issues  S_t = Q_t K^T  (M 128, N SP, K 64; t = query tile 0 / 1) into TMEM, and after
-//                 the softmax warps published P_t,  O_t = P_t V  (M 128, N 64, K SP; V is the MN-major B operand
-//                 straight from its [key][d] rows)
-//     warps 2-9   two softmax groups, group t owns query tile t: a thread owns ONE query row (TMEM lane), so row
-//                 max / row sum need no shuffles; two passes over the row in TMEM (max, then exp2 + sum + the
-//                 counter-hash dropout of attention.cu), P written as bf16 into the K-major SWIZZLE_128B
-//                 shared-memory layout the MMA's A descriptor reads; then the epilogue O / rowsum -> ctx, lse.
-//   TMEM: S_0 [0,160) S_1 [192,352) O_0 [384,448) O_1 [448,512) of 512 columns.
-//
-// STATUS: written and compiled (ptxas / SASS checked) at the end of round 1 after the round's GPU budget was
-// spent -- NOT YET RUN ON HARDWARE.  It is therefore off by default: uc2_attention_fwd(_dropout) only route here
-// after uc2_attention_tc_enable(1) or with UC2_ATTN_TCGEN05=1 in the environment, and its parity test
-// (tests/test_attention_tc_gpu.py) runs only with UC2_TEST_EXPERIMENTAL=1.  Results are defined to be those of
-// attention_fwd_bh_kernel (same masks, same dropout stream, same lse), so the existing backward pairs with it.
-// Checked on the CPU meanwhile (tests/test_attention_tc_{layout,protocol,dataflow}_cpu.py): every MMA operand as
-// read through its descriptor, the mbarrier protocol under random interleavings, and the data path on real numbers.
-// If you change an offset, a stride, a barrier count or a parity here, change the mirrored constant there.
+// tcgen05 / TMEM attention, forward (S <= 256) and backward (S <= 160), 12 heads x 64: the default kernels behind
+// uc2_attention_fwd* / _bwd* for those lengths.  Replaces the same reference code as attention.cu
+// (BertSelfAttention.forward model/layer.py:80-100) with every product on the 5th-generation tensor cores:
+// accumulators in tensor memory, operands by TMA (SWIZZLE_128B), the forward's P kept in tensor memory as the TMEM-A
+// operand of P V.  Each kernel's own comment block describes its pipeline.  First run on hardware in round 2; parity
+// against a torch fp32 restatement, against the mma.sync kernels and through the whole model is in
+// tests/test_attention_tc_gpu.py, tests/test_attention_gpu.py and tests/test_model_gpu.py; profiles/r02_* hold the
+// ncu captures.  UC2_ATTN_PROF=1 prints per-warp phase cycle counters (debug only; it synchronises).
 #include <atomic>
 #include <mutex>
 #include <stdlib.h>
@@ -530,8 +513,10 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
 //     element-wise: P = exp2(s - lse), dropout, dS = P (dP - delta)       -> Pd^T_u, dS^T_u as bf16 K-major tiles
 //     dV_u = Pd^T_u dO, dK_u = dS^T_u Q / 8                                (M 128, N 64, K SP; alias TMEM [0,64) [64,128))
 //     dQ_m += dS_u K_u / 8  for the query tiles m                         (A = the dS^T tile read MN-major; TMEM [384,512))
-// Tiles of Q, K, V, dO come by TMA once per item (single buffered: the next item's loads fly under this item's
-// last epilogues); 8 element-wise warps = 4 TMEM lane quarters x 2 column halves.
+// Tiles of Q, K, V, dO and O come by TMA once per item (single buffered; the next item's tiles are prefetched into
+// L2 meanwhile); delta is the row-wise dot product of the dO and O tiles (both carry the same swizzle).  16
+// element-wise warps = 4 TMEM lane quarters x 4 column parts; the dropout mask is the forward's (16 x 16 block hash,
+// common.cuh), here with the key as the per-thread factor and the query as the compile-time one.
 // =================================================================================================
 struct TcBwdParams {
     const long long* mask;
@@ -542,29 +527,44 @@ struct TcBwdParams {
     int B, S, SP, items;
     DropCfg drop;
     long long* prof;      // debug (UC2_ATTN_PROF=1), see TcParams
+    int blocks;           // 0: query blocks chosen from SP; 2: two blocks also for 128 < SP <= 160 (tuning knob)
 };
 
 struct TcBwdSmem {
-    uint32_t tile_bytes, pt_bytes, off_ds, off_pd, off_vec, off_bar, total;
-    int nu, nchunk;
+    uint32_t tile_bytes, pt_bytes, off_o, off_ds, off_pd, off_vec, off_bar, total;
+    uint32_t tm_s, tm_dp, tm_dv, tm_dk, tm_dq;
+    int nu, nv, nchunk;
 };
-__host__ __device__ inline TcBwdSmem tc_bwd_smem(int S, int SP) {
+// Two shapes of the same pipeline:
+//   SP <= 160  one query block (nv = 1): S^T_u and dP^T_u hold all SP query columns (TMEM [0,SP) and [192,192+SP)), dV_u / dK_u
+//              reuse the S^T columns [0,128) once the element-wise warps are through, dQ lives in [384,512)
+//   SP <= 256  two query blocks of <= 128 queries (nv = 2): S^T_uv [0,128), dP^T_uv [128,256), dV_u [256,320) and dK_u
+//              [320,384) accumulate over the blocks, dQ [384,512); the O tile (only needed for delta at the start of an
+//              item) shares its shared memory with the dS^T / Pd^T tiles, which hold one query block at a time
+__host__ __device__ inline TcBwdSmem tc_bwd_smem(int S, int SP, int blocks = 0) {
     TcBwdSmem L;
+    const bool wide = SP > 160 || (blocks == 2 && SP > 128);
     L.nu = S > 128 ? 2 : 1;
-    L.nchunk = (SP + 63) >> 6;
+    L.nv = wide ? 2 : 1;
+    L.nchunk = wide ? 2 : (SP + 63) >> 6;
     L.tile_bytes = SP * 128u;
     L.pt_bytes = L.nchunk * P_CHUNK_BYTES;
-    L.off_ds = 5u * L.tile_bytes;            // [Q][K][V][dO][O] then dS^T, then Pd^T (so MN-major over-reads of dS^T
-    L.off_pd = L.off_ds + L.pt_bytes;        // for the padding query blocks of dQ stay inside the allocation)
-    L.off_vec = L.off_pd + L.pt_bytes;       // 2 buffers x (lse2[SP], delta[SP])
+    L.off_ds = (wide ? 4u : 5u) * L.tile_bytes;      // [Q][K][V][dO]([O]) then dS^T, then Pd^T (so MN-major over-reads of
+    L.off_pd = L.off_ds + L.pt_bytes;                // dS^T for the padding query blocks of dQ stay inside the allocation)
+    L.off_o = wide ? L.off_ds : 4u * L.tile_bytes;
+    L.off_vec = L.off_pd + L.pt_bytes;               // 2 buffers x (lse2[SP], delta[SP])
     L.off_bar = L.off_vec + 4u * SP * 4u;
     L.total = 1024u + L.off_bar + 128u;
+    L.tm_s = 0u;
+    L.tm_dp = wide ? 128u : 192u;
+    L.tm_dv = wide ? 256u : 0u;
+    L.tm_dk = L.tm_dv + 64u;
+    L.tm_dq = 384u;
     return L;
 }
 
-constexpr int TC_BWD_MAX_SP = 160;
+constexpr int TC_BWD_MAX_SP = 256;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TMB_S = 0, TMB_DP = 192, TMB_DV = 0, TMB_DK = 64, TMB_DQ = 384;
 
 // W (16, 32 or 64) accumulator columns of this thread's row, times `scale`, -> W bf16 at dst
 template <int W>
@@ -596,7 +596,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
     const int S = p.S, SP = p.SP;
-    const TcBwdSmem L = tc_bwd_smem(S, SP);
+    const TcBwdSmem L = tc_bwd_smem(S, SP, p.blocks);
     float* vec = reinterpret_cast<float*>(gen + L.off_vec);          // [buf][lse2 SP | delta SP]
     const uint32_t bar = base + L.off_bar;
     // barriers (8 B each): ld_full ld_empty sd_full[2] pds_full[2] kv_full[2] s_empty[2] dq_full dq_empty, TMEM ptr
@@ -641,8 +641,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
 
     const uint32_t sQ = base, sK = sQ + L.tile_bytes, sV = sK + L.tile_bytes, sdO = sV + L.tile_bytes;
     const uint8_t* gdO = gen + 3u * L.tile_bytes;        // generic-address views of the dO and O tiles (delta)
-    const uint8_t* gO = gen + 4u * L.tile_bytes;
+    const uint8_t* gO = gen + L.off_o;
     const uint32_t sDS = base + L.off_ds, sPD = base + L.off_pd;
+    const int nv = L.nv;
+    auto nq_of = [&](int v) { return nv == 1 ? SP : (v == 0 ? 128 : SP - 128); };    // queries of block v
 
     if (warp == 0) {
         // ===================================== producer =====================================
@@ -656,7 +658,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 ptx::tma_load_2d(sK, &tmap_qkv, ld_full, HID + h * HD, b * S);
                 ptx::tma_load_2d(sV, &tmap_qkv, ld_full, 2 * HID + h * HD, b * S);
                 ptx::tma_load_2d(sdO, &tmap_do, ld_full, h * HD, b * S);
-                ptx::tma_load_2d(sdO + L.tile_bytes, &tmap_o, ld_full, h * HD, b * S);
+                ptx::tma_load_2d(base + L.off_o, &tmap_o, ld_full, h * HD, b * S);
                 const int nxt = item + gridDim.x;                  // warm L2 with the next item's tiles
                 if (nxt < p.items) {
                     const int nb = nxt / NH, nh = nxt - nb * NH;
@@ -671,7 +673,6 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     } else if (warp == 1) {
         // ===================================== MMA issuer ===================================
         if (lane == 0) {
-            const uint32_t idesc_s = ptx::idesc_bf16_f32(128, SP, false, false);
             const uint32_t idesc_kv = ptx::idesc_bf16_f32(128, HD, false, true);
             const uint32_t idesc_dq = ptx::idesc_bf16_f32(128, HD, true, true);
             PhaseClock pc(p.prof, bwd_threads(NSPLIT) / 32);
@@ -683,62 +684,71 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 pc.lap(1);
                 ptx::tc_fence_after();
                 for (int u = 0; u < nu; ++u) {
-                    // TMEM [0,352) is free once the dV / dK of the previous key tile have been read out
+                    // the dV / dK of the previous key tile have been read out (they share columns with S^T when nv == 1)
                     pc.lap(0);
                     if (u == 0) ptx::mbar_wait(s_empty(nu - 1), itp ^ 1u);
                     else ptx::mbar_wait(s_empty(u - 1), itp);
                     pc.lap(2);
                     ptx::tc_fence_after();
-                    // key tile 1 reads 128 rows from row 128 of K / V on; rows past SP are the following tiles
-                    // Consecutive products into the SAME accumulator run as a dependent chain (~80-90 cycles each
-                    // at these small N): products of independent accumulators are interleaved throughout.
-                    {
-                        const uint64_t dk = ptx::smem_desc_sw128(sK + u * 16384u, 16u, 1024u), dq = ptx::smem_desc_sw128(sQ, 16u, 1024u);
-                        const uint64_t dv = ptx::smem_desc_sw128(sV + u * 16384u, 16u, 1024u), dd = ptx::smem_desc_sw128(sdO, 16u, 1024u);
+                    const int ksteps = (u == 0 ? (SP < 128 ? SP : 128) : SP - 128) / 16;       // keys of this tile / 16
+                    for (int v = 0; v < nv; ++v) {
+                        const uint32_t ph = static_cast<uint32_t>(it * nv + v) & 1u;
+                        const int nq = nq_of(v) / 16;                                        // queries of this block / 16
+                        const uint32_t idesc_s = ptx::idesc_bf16_f32(128, nq * 16, false, false);
+                        // S^T_uv = K_u Q_v^T, dP^T_uv = V_u dO_v^T.  Key tile 1 reads 128 rows from row 128 of K / V on;
+                        // rows past SP are the following tiles.  Products of independent accumulators are interleaved.
+                        {
+                            const uint64_t dk = ptx::smem_desc_sw128(sK + u * 16384u, 16u, 1024u);
+                            const uint64_t dq = ptx::smem_desc_sw128(sQ + v * 16384u, 16u, 1024u);
+                            const uint64_t dv = ptx::smem_desc_sw128(sV + u * 16384u, 16u, 1024u);
+                            const uint64_t dd = ptx::smem_desc_sw128(sdO + v * 16384u, 16u, 1024u);
 #pragma unroll
-                        for (int k = 0; k < HD / 16; ++k) {          // + 32 bytes (2 in the address field) per 16 of head dim
-                            ptx::umma_bf16(tmem_base + TMB_S, dk + 2u * k, dq + 2u * k, idesc_s, k > 0 ? 1u : 0u);
-                            ptx::umma_bf16(tmem_base + TMB_DP, dv + 2u * k, dd + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                            for (int k = 0; k < HD / 16; ++k) {      // + 32 bytes (2 in the address field) per 16 of head dim
+                                ptx::umma_bf16(tmem_base + L.tm_s, dk + 2u * k, dq + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                                ptx::umma_bf16(tmem_base + L.tm_dp, dv + 2u * k, dd + 2u * k, idesc_s, k > 0 ? 1u : 0u);
+                            }
                         }
-                    }
-                    ptx::umma_commit(sd_full(u));
-                    pc.lap(3);
+                        ptx::umma_commit(sd_full(u));
+                        pc.lap(3);
 
-                    ptx::mbar_wait(pds_full(u), itp);              // Pd^T_u, dS^T_u written; S^T, dP^T read
-                    pc.lap(4);
-                    if (u == 0) ptx::mbar_wait(dq_empty, itp ^ 1u);   // previous item's dQ read out
-                    pc.lap(5);
-                    ptx::tc_fence_after();
-                    // dV_u = Pd^T_u dO, dK_u = dS^T_u Q (K dimension = queries: A = the K-major tiles the element-wise warps
-                    // wrote, B = dO / Q rows, MN-major) and dQ_m += dS[queries of tile m, keys of tile u] K_u (A = the dS^T
-                    // tile read MN-major: 64-query blocks P_CHUNK_BYTES apart, 16 key rows per K step; B = K rows of tile
-                    // u, MN-major): up to four independent accumulators, one K step of each per round
-                    {
-                        const int nq = SP / 16;
-                        const int ksteps = (u == 0 ? (SP < 128 ? SP : 128) : SP - 128) / 16;
-                        const uint64_t b_do = ptx::smem_desc_sw128(sdO, 8192u, 1024u), b_q = ptx::smem_desc_sw128(sQ, 8192u, 1024u);
-                        const uint64_t b_k = ptx::smem_desc_sw128(sK + u * 16384u, 8192u, 1024u);
-                        const uint64_t a_dq0 = ptx::smem_desc_sw128(sDS, P_CHUNK_BYTES, 1024u);
-                        const uint64_t a_dq1 = ptx::smem_desc_sw128(sDS + 2u * P_CHUNK_BYTES, P_CHUNK_BYTES, 1024u);
-                        const int rounds = nq > ksteps ? nq : ksteps;
-                        for (int kk = 0; kk < rounds; ++kk) {
-                            if (kk < nq) {
-                                const uint32_t a_off = (kk >> 2) * P_CHUNK_BYTES + (kk & 3) * 32u;
-                                ptx::umma_bf16(tmem_base + TMB_DV, ptx::smem_desc_sw128(sPD + a_off, 16u, 1024u),
-                                               b_do + 128u * kk, idesc_kv, kk > 0 ? 1u : 0u);
-                                ptx::umma_bf16(tmem_base + TMB_DK, ptx::smem_desc_sw128(sDS + a_off, 16u, 1024u),
-                                               b_q + 128u * kk, idesc_kv, kk > 0 ? 1u : 0u);
-                            }
-                            if (kk < ksteps) {
-                                const uint32_t acc = (u > 0 || kk > 0) ? 1u : 0u;
-                                ptx::umma_bf16(tmem_base + TMB_DQ, a_dq0 + 128u * kk, b_k + 128u * kk, idesc_dq, acc);
-                                if (nu == 2)
-                                    ptx::umma_bf16(tmem_base + TMB_DQ + 64u, a_dq1 + 128u * kk, b_k + 128u * kk, idesc_dq, acc);
+                        ptx::mbar_wait(pds_full(u), ph);               // Pd^T_uv, dS^T_uv written; S^T, dP^T read
+                        pc.lap(4);
+                        if (u == 0 && v == 0) ptx::mbar_wait(dq_empty, itp ^ 1u);   // previous item's dQ read out
+                        pc.lap(5);
+                        ptx::tc_fence_after();
+                        // dV_u (+)= Pd^T_uv dO_v, dK_u (+)= dS^T_uv Q_v (K dimension = the block's queries: A = the K-major
+                        // tiles the element-wise warps wrote, B = dO / Q rows, MN-major) and dQ (+)= dS K_u for the query
+                        // tiles the block covers (A = the dS^T tile read MN-major: 64-query blocks P_CHUNK_BYTES apart,
+                        // 16 key rows per K step; B = K rows of tile u, MN-major): one K step of each per round
+                        {
+                            const uint64_t b_do = ptx::smem_desc_sw128(sdO + v * 16384u, 8192u, 1024u);
+                            const uint64_t b_q = ptx::smem_desc_sw128(sQ + v * 16384u, 8192u, 1024u);
+                            const uint64_t b_k = ptx::smem_desc_sw128(sK + u * 16384u, 8192u, 1024u);
+                            const uint64_t a_dq0 = ptx::smem_desc_sw128(sDS, P_CHUNK_BYTES, 1024u);
+                            const uint64_t a_dq1 = ptx::smem_desc_sw128(sDS + 2u * P_CHUNK_BYTES, P_CHUNK_BYTES, 1024u);
+                            const bool two_dq = nv == 1 && nu == 2;       // one block holding both query tiles
+                            const uint32_t dq_col = L.tm_dq + (nv == 2 ? 64u * v : 0u);
+                            const int rounds = nq > ksteps ? nq : ksteps;
+                            for (int kk = 0; kk < rounds; ++kk) {
+                                if (kk < nq) {
+                                    const uint32_t a_off = (kk >> 2) * P_CHUNK_BYTES + (kk & 3) * 32u;
+                                    const uint32_t acc = (v > 0 || kk > 0) ? 1u : 0u;
+                                    ptx::umma_bf16(tmem_base + L.tm_dv, ptx::smem_desc_sw128(sPD + a_off, 16u, 1024u),
+                                                   b_do + 128u * kk, idesc_kv, acc);
+                                    ptx::umma_bf16(tmem_base + L.tm_dk, ptx::smem_desc_sw128(sDS + a_off, 16u, 1024u),
+                                                   b_q + 128u * kk, idesc_kv, acc);
+                                }
+                                if (kk < ksteps) {
+                                    const uint32_t acc = (u > 0 || kk > 0) ? 1u : 0u;
+                                    ptx::umma_bf16(tmem_base + dq_col, a_dq0 + 128u * kk, b_k + 128u * kk, idesc_dq, acc);
+                                    if (two_dq)
+                                        ptx::umma_bf16(tmem_base + L.tm_dq + 64u, a_dq1 + 128u * kk, b_k + 128u * kk, idesc_dq, acc);
+                                }
                             }
                         }
+                        pc.lap(6);
                     }
                     ptx::umma_commit(kv_full(u));
-                    pc.lap(6);
                 }
                 ptx::umma_commit(ld_empty);
                 ptx::umma_commit(dq_full);
@@ -752,8 +762,6 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
         const int kr = q * 32 + lane;                   // row inside a 128-row tile
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
-        const int nch = SP / 16, per = (nch + NSPLIT - 1) / NSPLIT;          // 16-column chunks per part
-        const int c_begin = min(part * per, nch) * 16, c_end = min((part + 1) * per, nch) * 16;
         PhaseClock pc(p.prof, bwd_threads(NSPLIT) / 32);
         int it = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
@@ -798,68 +806,75 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 const int key = u * 128 + kr;
                 const bool key_ok = key < S;
                 const float bias = key_ok ? (p.mask[row0 + key] != 0 ? 0.f : MASK_LOG2) : -INFINITY;
-                pc.lap(0);
-                ptx::mbar_wait(sd_full(u), itp);
-                pc.lap(2);
-                ptx::tc_fence_after();
                 const uint32_t prow = static_cast<uint32_t>(kr) * 128u;
                 // dropout (common.cuh "Attention-probability dropout"): this thread's key contributes CB^(key & 15)
                 const uint32_t bpow = drop_pow_rt(DROP_CB, static_cast<uint32_t>(key)), jblk = static_cast<uint32_t>(key) >> 4;
                 const uint32_t t32 = p.drop.thresh << 16;
-                for (int c = c_begin; c < c_end; c += 16) {
-                    uint32_t rs[16], rd[16], pd[8], ds[8];
-                    ptx::tmem_ld_32x16(tmem_base + lane_sel + TMB_S + c, rs);
-                    ptx::tmem_ld_32x16(tmem_base + lane_sel + TMB_DP + c, rd);
-                    const uint32_t rbase = p.drop.thresh ? drop_block_hash(hkey, static_cast<uint32_t>(c) >> 4, jblk) * bpow : 0u;
-                    ptx::tmem_wait_ld();
+                for (int v = 0; v < nv; ++v) {
+                    const uint32_t ph = static_cast<uint32_t>(it * nv + v) & 1u;
+                    const int q_base = v * 128;                                        // first query of the block
+                    const int nch = nq_of(v) / 16, per = (nch + NSPLIT - 1) / NSPLIT;   // 16-column chunks per part
+                    const int c_begin = min(part * per, nch) * 16, c_end = min((part + 1) * per, nch) * 16;
+                    pc.lap(0);
+                    ptx::mbar_wait(sd_full(u), ph);
+                    pc.lap(2);
+                    ptx::tc_fence_after();
+                    for (int c = c_begin; c < c_end; c += 16) {
+                        uint32_t rs[16], rd[16], pd[8], ds[8];
+                        ptx::tmem_ld_32x16(tmem_base + lane_sel + L.tm_s + c, rs);
+                        ptx::tmem_ld_32x16(tmem_base + lane_sel + L.tm_dp + c, rd);
+                        const uint32_t rbase =
+                            p.drop.thresh ? drop_block_hash(hkey, static_cast<uint32_t>(q_base + c) >> 4, jblk) * bpow : 0u;
+                        ptx::tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c + j);
-                        const float4 d4 = *reinterpret_cast<const float4*>(delta + c + j);
-                        const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq[4] = {d4.x, d4.y, d4.z, d4.w};
-                        float pdv[4], dsv[4];
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 l4 = *reinterpret_cast<const float4*>(lse2 + q_base + c + j);
+                            const float4 d4 = *reinterpret_cast<const float4*>(delta + q_base + c + j);
+                            const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq[4] = {d4.x, d4.y, d4.z, d4.w};
+                            float pdv[4], dsv[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float pe = fast_ex2(fmaf(__uint_as_float(rs[j + e]), SCALE_LOG2, bias) - lq[e]);
-                            float dp = __uint_as_float(rd[j + e]);
-                            pdv[e] = pe;
-                            if (p.drop.thresh) {
-                                // element (query c + j + e, key): same stream as the forward
-                                const float sc = rbase * drop_pow(DROP_CA, j + e) >= t32 ? p.drop.scale : 0.f;   // finite operands only
-                                pdv[e] = pe * sc;
-                                dp *= sc;
+                            for (int e = 0; e < 4; ++e) {
+                                const float pe = fast_ex2(fmaf(__uint_as_float(rs[j + e]), SCALE_LOG2, bias) - lq[e]);
+                                float dp = __uint_as_float(rd[j + e]);
+                                pdv[e] = pe;
+                                if (p.drop.thresh) {
+                                    // element (query q_base + c + j + e, key): same stream as the forward
+                                    const float sc = rbase * drop_pow(DROP_CA, j + e) >= t32 ? p.drop.scale : 0.f;   // finite operands only
+                                    pdv[e] = pe * sc;
+                                    dp *= sc;
+                                }
+                                // dS without the 1/sqrt(64): a power of two commutes with the bf16 rounding, so it is
+                                // applied once per OUTPUT element in the dK / dQ epilogues instead of once per score here
+                                dsv[e] = pe * (dp - dq[e]);
                             }
-                            // dS without the 1/sqrt(64): a power of two commutes with the bf16 rounding, so it is applied
-                            // once per OUTPUT element in the dK / dQ epilogues instead of once per score here
-                            dsv[e] = pe * (dp - dq[e]);
+                            pd[j / 2] = pack_bf16(pdv[0], pdv[1]);
+                            pd[j / 2 + 1] = pack_bf16(pdv[2], pdv[3]);
+                            ds[j / 2] = pack_bf16(dsv[0], dsv[1]);
+                            ds[j / 2 + 1] = pack_bf16(dsv[2], dsv[3]);
                         }
-                        pd[j / 2] = pack_bf16(pdv[0], pdv[1]);
-                        pd[j / 2 + 1] = pack_bf16(pdv[2], pdv[3]);
-                        ds[j / 2] = pack_bf16(dsv[0], dsv[1]);
-                        ds[j / 2 + 1] = pack_bf16(dsv[2], dsv[3]);
-                    }
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const uint32_t q0 = c + 8 * g;             // 8 queries = one 16-byte unit of the swizzled row
-                        const uint32_t off = (q0 >> 6) * P_CHUNK_BYTES + prow + ((((q0 & 63u) >> 3) ^ sw) << 4);
-                        ptx::st_shared_v4(sPD + off, pd[4 * g], pd[4 * g + 1], pd[4 * g + 2], pd[4 * g + 3]);
-                        ptx::st_shared_v4(sDS + off, ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]);
+                        for (int g = 0; g < 2; ++g) {
+                            const uint32_t q0 = c + 8 * g;         // 8 queries = one 16-byte unit of the swizzled row
+                            const uint32_t off = (q0 >> 6) * P_CHUNK_BYTES + prow + ((((q0 & 63u) >> 3) ^ sw) << 4);
+                            ptx::st_shared_v4(sPD + off, pd[4 * g], pd[4 * g + 1], pd[4 * g + 2], pd[4 * g + 3]);
+                            ptx::st_shared_v4(sDS + off, ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]);
+                        }
                     }
+                    ptx::fence_proxy_async();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(pds_full(u));
+                    pc.lap(3);
                 }
-                ptx::fence_proxy_async();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(pds_full(u));
-                pc.lap(3);
 
-                // this key row's [dV_u | dK_u] = TMEM columns [0,128): part -> a 128 / NSPLIT-column slice -> dqkv
+                // this key row's [dV_u | dK_u] = 128 adjacent TMEM columns: part -> a 128 / NSPLIT-column slice -> dqkv
                 ptx::mbar_wait(kv_full(u), itp);
                 pc.lap(4);
                 ptx::tc_fence_after();
                 constexpr int WKV = 128 / NSPLIT;
                 const int ckv = part * WKV;
                 bf16* dst = p.dqkv + (row0 + key) * QKV_LD + (ckv < HD ? 2 * HID : HID) + h * HD + (ckv & (HD - 1));
-                store_cols<WKV>(tmem_base + lane_sel + TMB_DV + ckv, dst, key_ok, ckv < HD ? 1.f : 0.125f);
+                store_cols<WKV>(tmem_base + lane_sel + L.tm_dv + ckv, dst, key_ok, ckv < HD ? 1.f : 0.125f);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(s_empty(u));
@@ -873,11 +888,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 pc.lap(6);
                 ptx::tc_fence_after();
                 constexpr int WQ = HD / NSPLIT;
-                store_cols<WQ>(tmem_base + lane_sel + TMB_DQ + part * WQ,
+                store_cols<WQ>(tmem_base + lane_sel + L.tm_dq + part * WQ,
                                p.dqkv + (row0 + kr) * QKV_LD + h * HD + part * WQ, kr < S, 0.125f);
-                if (nu == 2 && q == 0)
-                    store_cols<WQ>(tmem_base + TMB_DQ + 64u + part * WQ,
-                                   p.dqkv + (row0 + 128 + lane) * QKV_LD + h * HD + part * WQ, 128 + lane < S, 0.125f);
+                if (nu == 2 && 128 + q * 32 < S)       // second query tile: rows 128 + (this lane quarter's rows)
+                    store_cols<WQ>(tmem_base + lane_sel + L.tm_dq + 64u + part * WQ,
+                                   p.dqkv + (row0 + 128 + kr) * QKV_LD + h * HD + part * WQ, 128 + kr < S, 0.125f);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(dq_empty);
@@ -1011,14 +1026,16 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     if (int rc = make_tmap(&tq, qkv, (long long)B * S, QKV_LD, QKV_LD, SP)) return rc;
     if (int rc = make_tmap(&tdo, dctx, (long long)B * S, HID, HID, SP)) return rc;
     if (int rc = make_tmap(&to, ctx, (long long)B * S, HID, HID, SP)) return rc;
-    const TcBwdSmem L = tc_bwd_smem(S, SP);
+    static const int blocks = [] { const char* e = getenv("UC2_ATTN_TC_BWD_BLOCKS"); return (e && e[0] == '2') ? 2 : 0; }();
+    const TcBwdSmem L = tc_bwd_smem(S, SP, blocks);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     static int nsplit = 4;
     std::call_once(once, [] {
         const char* e = getenv("UC2_ATTN_TC_BWD_SPLIT");          // tuning knob: 4 (default) or 2 warps per lane quarter
         if (e && e[0] == '2') nsplit = 2;
-        const int bytes = static_cast<int>(tc_bwd_smem(TC_BWD_MAX_SP, TC_BWD_MAX_SP).total);
+        const uint32_t b_wide = tc_bwd_smem(TC_BWD_MAX_SP, TC_BWD_MAX_SP).total, b_narrow = tc_bwd_smem(160, 160).total;
+        const int bytes = static_cast<int>(b_wide > b_narrow ? b_wide : b_narrow);
         attr_err = cudaFuncSetAttribute(attention_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(attention_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -1033,6 +1050,7 @@ extern "C" UC2_API int uc2_attention_bwd_tc(const void* qkv, const long long* at
     p.dqkv = static_cast<bf16*>(dqkv);
     p.B = B; p.S = S; p.SP = SP; p.items = B * NH;
     p.drop = DropCfg{drop_key, drop_thresh, drop_scale};
+    p.blocks = blocks;
     const int grid = p.items < num_sms() ? p.items : num_sms();
     p.prof = nullptr;
     static const bool prof_on = [] { const char* e = getenv("UC2_ATTN_PROF"); return e && e[0] == '1'; }();

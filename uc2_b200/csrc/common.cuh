@@ -45,7 +45,7 @@ struct ProfScope {
 int require_sm100();
 bool pdl_enabled();      // programmatic dependent launch (off with UC2_NO_PDL=1)
 bool attn_tc_enabled();  // tcgen05 attention kernels (attention_tc.cu) in use; UC2_ATTN_TCGEN05=0 switches them off
-inline bool attn_tc_bwd_serves(int S) { return (S + 15) / 16 * 16 <= 160; }   // shapes uc2_attention_bwd_tc takes
+inline bool attn_tc_bwd_serves(int S) { return (S + 15) / 16 * 16 <= 256; }   // shapes uc2_attention_bwd_tc takes
 
 // Launch `kern` allowing it to start while the previous kernel of the stream is still draining (programmatic
 // dependent launch): its CTAs may become resident and run their prologue early, and MUST call griddep_wait()
