@@ -447,7 +447,8 @@ def run_training(args, workload, rank, world, steps, warmup, with_cpu, with_stor
     opt = AdamW(groups, lr=LR, betas=BETAS, lazy_rows=not args.eager_adamw)
     step_fn = TrainStep(model, opt, grad_norm=GRAD_NORM,
                         lr_fn=lambda s: max(LR * warmup_linear(s, WARMUP_STEPS, TRAIN_STEPS), 1e-8),
-                        grad_comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else None)
+                        grad_comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else None,
+                        grad_overlap=not args.no_grad_overlap)
 
     host = [(t, pin(b)) for t, b in host_batches(workload, 1000 + rank)]
     resident = [(t, UB.to_device(b, dev)) for t, b in host]
@@ -515,6 +516,21 @@ def run_training(args, workload, rank, world, steps, warmup, with_cpu, with_stor
     for i in range(n_warm):
         warm(i)
     ms_e2e = timed(e2e_run(steps), steps)
+
+    if os.environ.get("UC2_BENCH_BREAKDOWN") == "1":
+        # debug: where a step's time goes (forward + backward incl. overlapped exchange | exposed exchange | clip + AdamW)
+        step_fn.trace = []
+        for i in range(2 * len(resident)):
+            step_resident(i)
+        torch.cuda.synchronize()
+        agg = {}
+        for t, ev in step_fn.trace:
+            agg.setdefault(t, []).append([ev[k].elapsed_time(ev[k + 1]) for k in range(3)])
+        for t, v in agg.items():
+            m = np.mean(np.array(v), 0)
+            print(f"[rank {rank}] breakdown task={t}: fwd+bwd {m[0]:.2f} ms, exposed exchange {m[1]:.2f} ms, optimizer {m[2]:.2f} ms",
+                  file=sys.stderr, flush=True)
+        step_fn.trace = None
 
     # The same step fed from an HBM-resident feature store (uc2_b200.device_batch): the host sends
     # token ids and three integers per sample, the padded batch is assembled by uc2_pad_rows / uc2_batch_index.
@@ -640,7 +656,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="hidden / attention dropout of the training workloads (config/uc2-base.json: 0.1)")
-    ap.add_argument("--grad-comm", default="bf16", choices=["bf16", "fp32"],
+    ap.add_argument("--no-grad-overlap", action="store_true",
+                    help="exchange gradients after the backward pass instead of under it")
+    ap.add_argument("--grad-comm", default="fp32", choices=["bf16", "fp32"],
                     help="wire type of the gradient exchange at N > 1 (the reference exchanges fp16 gradients)")
     ap.add_argument("--eager-adamw", action="store_true",
                     help="update every vocabulary row in every step instead of deferring rows without gradient")

@@ -109,6 +109,11 @@ UC2_API int uc2_ce_stats_reduce(const float* stats, long long ld_ce, int n_chunk
 UC2_API int uc2_ce_bwd_inplace_bf16(void* logits_bf16, long long ld, long long rows, int C, const long long* targets,
                                     long long ignore_index, const float* dloss, const float* lse, void* stream);
 
+/* Persistent kernels (GEMM, attention, LayerNorm backward, ...) size their grids for every SM of the device minus n
+ * (even, <= 64; UC2_RESERVE_SMS in the environment sets the initial value).  Data-parallel training sets aside the SMs
+ * it lets NCCL use, so that neither side waits for an SM the other holds.  Returns the previous value. */
+UC2_API int uc2_reserve_sms(int n);
+
 /* ---------------------------------------------------------------------------------------------
  * Embeddings fused with the gather_index pack.
  * Replaces {VLXLMR,Uniter}TextEmbeddings.forward (model/model.py:304-335, 987-1001),

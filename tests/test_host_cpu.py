@@ -779,3 +779,45 @@ def test_whole_collates_match_reference(golden):
     tok_soft = [torch.softmax(torch.from_numpy(synth.det_normal((nb, 16), 71 * 5 + i, 2.0)).float(), -1)
                 for i, nb in enumerate(nbbs)]
     _check_batch(g, "mmxlm_soft", B.collate_mmxlm_soft(items, masks, tok_soft))
+
+
+def test_attention_dropout_block_stream_host_mirror():
+    """uc2_b200/dropout.py attn_keep_mask_np (the tcgen05 attention kernels' mask, csrc/common.cuh): deterministic, the
+    documented formula element by element, keep rate p, and no structure a dropout user would notice (block drop counts
+    binomial, neighbours uncorrelated)."""
+    from uc2_b200 import dropout as DO
+    p, S = 0.1, 160
+    t = DO.thresh_of(p)
+    key = DO.head_key(0xABCDEF, 7)
+    m = DO.attn_keep_mask_np(key, S, t)
+    assert m.shape == (S, S) and np.array_equal(m, DO.attn_keep_mask_np(key, S, t))
+    for i, j in ((0, 0), (5, 9), (17, 31), (159, 159), (100, 3)):
+        h = DO.lowbias32(key ^ (((i >> 4) << 16) | (j >> 4)))
+        e = (h * pow(DO.ATTN_CA, i & 15, 1 << 32) * pow(DO.ATTN_CB, j & 15, 1 << 32)) & DO.M32
+        assert bool(m[i, j]) == (e >= (t << 16))
+    masks = np.stack([DO.attn_keep_mask_np(DO.head_key(0x1234, bh), S, t) for bh in range(96)])
+    assert abs(masks.mean() - (1 - DO.thresh_of(p) / 65536.0)) < 2e-3
+    drops = (~masks).reshape(96, 10, 16, 10, 16).sum((2, 4)).ravel()
+    assert abs(drops.var() / (256 * 0.1 * 0.9) - 1) < 0.1                     # binomial block counts
+    flat = masks.astype(np.float64)
+    assert abs(np.corrcoef(flat[:, :, :-1].ravel(), flat[:, :, 1:].ravel())[0, 1]) < 5e-3
+    assert abs(np.corrcoef(flat[:, :-1].ravel(), flat[:, 1:].ravel())[0, 1]) < 5e-3
+    assert DO.attn_keep_mask_np(key, 33, 0).all()                              # thresh 0: dropout off
+
+
+def test_bench_workloads_host_side():
+    """bench.py builds the BASELINE configs it names: cfg3 task cycle at 64 x (60 + 100), cfg5 VTLM pairs at S = 222 with
+    TLM position ids restarting at the second <s> (data/mlm.py:420-428), and one row of work per workload."""
+    import bench
+    assert set(bench.WORKLOADS) == {"pretrain", "itm", "vtlm"}
+    hb = bench.host_batches("vtlm", seed=3, n=4)
+    assert [t for t, _ in hb] == ["tlm"]
+    b = hb[0][1]
+    assert b["attn_masks"].shape == (4, 222) and b["input_ids"].shape == (4, 122)
+    pos = b["position_ids"][0].tolist()
+    assert pos[:3] == [2, 3, 4] and pos[61] == 2 and pos[60] == 62          # restart at the second <s>
+    assert b["n_masked"] == int((b["txt_labels"] != -1).sum()) > 0
+    assert int(b["txt_labels"][:, 60].max()) == -1 and int(b["txt_labels"][:, 61].max()) == -1
+    pb = bench.host_batches("pretrain", seed=3, n=4)
+    assert [t for t, _ in pb] == list(bench.TASKS)
+    assert all(x["attn_masks"].shape == (4, 160) for _, x in pb)

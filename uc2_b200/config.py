@@ -48,6 +48,11 @@ class UC2Config(object):
                              f"{self.hidden_size}/{self.num_attention_heads}/{self.intermediate_size}")
         if self.hidden_act != "gelu":
             raise ValueError("only hidden_act='gelu' (erf form, model/layer.py:31-37) is implemented")
+        # packed sequences (text + regions) above 256 run on the tiled mma.sync attention kernels, which implement no
+        # attention-probability dropout: say so when the model is built, not at the first training step
+        if self.attention_probs_dropout_prob > 0 and getattr(self, "max_packed_len", 256) > 256:
+            raise ValueError("attention dropout is implemented for packed lengths up to 256; set max_packed_len <= 256 "
+                             "(every UC2 recipe: <= 122 tokens + 100 regions) or attention_probs_dropout_prob = 0")
 
 
 VLXLMRConfig = UC2Config

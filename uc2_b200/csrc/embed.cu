@@ -94,6 +94,9 @@ __device__ __forceinline__ Src resolve(const EmbedParams& p, int b, int j) {
     if (p.mode == 1) { s.is_img = 0; s.idx = j; return s; }
     if (p.mode == 2) { s.is_img = 1; s.idx = j; return s; }
     const long long g = p.gather_index[(long long)b * p.S + j];
+    // an index outside the concatenation [text; regions] would read (and, in the backward, write) outside the batch:
+    // fail the launch like nn.Embedding / torch.gather's device assert does
+    if (g < 0 || g >= p.T + p.R) asm volatile("trap;");
     if (g < p.T) { s.is_img = 0; s.idx = (int)g; } else { s.is_img = 1; s.idx = (int)(g - p.T); }
     return s;
 }
@@ -113,6 +116,8 @@ __device__ __forceinline__ int text_position(const EmbedParams& p, int b, int t,
 }
 
 __device__ __forceinline__ void text_presum(const EmbedParams& p, long long id, int pos, int lane, float* v) {
+    // token / position ids index the parameter (forward) and gradient (backward) tables directly: out of range = trap
+    if (id < 0 || id >= p.vocab || pos < 0 || pos >= p.max_pos) asm volatile("trap;");
     float a[VPL];
     load_row_f32(p.word_emb + id * HID, lane, v);
     load_row_f32(p.pos_emb + (long long)pos * HID, lane, a);

@@ -47,10 +47,21 @@ static int dev_query(int* sms, int* cc) {
     return 0;
 }
 
+// SMs the persistent kernels size their grids for: all of them, minus the ones set aside for communication kernels
+// that run concurrently (uc2_reserve_sms; data-parallel training hands NCCL a few CTAs -- a persistent GEMM whose grid
+// counts on every SM would otherwise wait for whichever SMs a collective is holding)
+static std::atomic<int> g_reserved_sms{-1};
 int num_sms() {
     int sms = 148, cc = 0;
     dev_query(&sms, &cc);
-    return sms;
+    int r = g_reserved_sms.load(std::memory_order_relaxed);
+    if (r < 0) {
+        const char* e = getenv("UC2_RESERVE_SMS");
+        r = e ? atoi(e) : 0;
+        if (r < 0 || r > sms / 2) r = 0;
+        g_reserved_sms.store(r, std::memory_order_relaxed);
+    }
+    return sms - r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -163,3 +174,9 @@ extern "C" UC2_API int uc2_profile_collect(double* ms_by_kind, double* work_by_k
 extern "C" UC2_API const char* uc2_last_error(void) { return uc2::g_err; }
 extern "C" UC2_API int uc2_version(void) { return 100; }
 extern "C" UC2_API long long uc2_launch_count(void) { return uc2::g_launches.load(); }
+
+extern "C" UC2_API int uc2_reserve_sms(int n) {
+    const int prev = uc2::g_reserved_sms.load(std::memory_order_relaxed);
+    uc2::g_reserved_sms.store(n < 0 ? 0 : (n > 64 ? 64 : n & ~1), std::memory_order_relaxed);
+    return prev < 0 ? 0 : prev;
+}

@@ -100,6 +100,11 @@ class GradSync(object):
         self.comm_dtype = comm_dtype if (comm_dtype is not None and flat_grad.is_cuda) else None
         self.comm = None        # persistent 16-bit staging buffer, same indexing as flat
         self.staged = []        # (work, lo, hi) buckets to copy back in finish()
+        self.after = []         # closures run by finish() once every bucket is back in the arena
+        self.overlap = True     # False: ready() only records the range; everything is exchanged in finish(), after the
+                                # backward pass (no NCCL kernel holds SMs while the persistent GEMMs run)
+        self.early_dense = True # tied-decoder steps: exchange the dense table gradient as soon as the decoder's wgrad is
+                                # written, the embedding lookup's rows separately at the end (side_rows)
 
     def _submit(self, s, e):
         if self.comm_dtype is None:
@@ -115,6 +120,8 @@ class GradSync(object):
         """The backward pass has finished writing flat[lo:hi]."""
         if not self.enabled or size() == 1 or hi <= lo:
             return
+        if not self.overlap:
+            return                          # finish() submits whatever was not reported
         self.done.append((lo, hi))
         for s in range(lo, hi, self.bucket):
             self._submit(s, min(s + self.bucket, hi))
@@ -162,6 +169,30 @@ class GradSync(object):
         self.last_ids = all_ids                      # every row that carries gradient after the exchange
         self.done.append((lo, lo + n_rows * width))
 
+    def side_rows(self, side, table, row_ids, pad_row=0):
+        """Steps whose vocabulary-table gradient has a dense term (the tied MLM decoder's wgrad) AND the embedding
+        lookup's row-sparse term: the dense term went out through ready() right after the decoder's backward and is
+        being averaged under the encoder's backward; the lookup rows were accumulated into `side` (a zero table of the
+        same shape) instead.  Exchange those rows like sparse_rows, clear them in `side`, and add their mean to
+        `table` in finish(), after the dense average has landed."""
+        W = size()
+        ids = row_ids.reshape(-1).to(torch.long)
+        cap = host_max(ids.numel())
+        if cap > ids.numel():
+            ids = torch.cat([ids, ids.new_full((cap - ids.numel(),), int(pad_row))])
+        ids, _ = ids.sort()
+        first = torch.ones_like(ids, dtype=torch.bool)
+        first[1:] = ids[1:] != ids[:-1]
+        rows = side.index_select(0, ids) * first.unsqueeze(1).to(side.dtype)
+        if self.comm_dtype is not None:
+            rows = rows.to(self.comm_dtype)
+        all_ids = torch.empty(W * ids.numel(), dtype=ids.dtype, device=ids.device)
+        all_rows = torch.empty((W * ids.numel(), rows.size(1)), dtype=rows.dtype, device=rows.device)
+        dist.all_gather_into_tensor(all_ids, ids)
+        dist.all_gather_into_tensor(all_rows, rows)
+        side.index_fill_(0, ids, 0)
+        self.after.append(lambda: table.index_add_(0, all_ids, all_rows.to(table.dtype), alpha=1.0 / W))
+
     def finish(self):
         """Submit whatever was not reported through ready(), then make the compute stream wait."""
         if self.enabled and size() > 1:
@@ -178,7 +209,9 @@ class GradSync(object):
         for w, s, e in self.staged:
             w.wait()
             self.flat[s:e].copy_(self.comm[s:e])
-        self.works, self.done, self.staged = [], [], []
+        for fn in self.after:
+            fn()
+        self.works, self.done, self.staged, self.after = [], [], [], []
 
 
 # --------------------------------------------------------------------------------------------------

@@ -184,8 +184,17 @@ def encoder_backward(enc, arena, st, dout):
     # embeddings
     g = _lib.EmbedGrads()
     names = []
+    dense_sent = st.mode != 2 and sync is not None and sync.enabled and getattr(arena, "word_dense_sent", False)
     if st.mode != 2:
-        g.word_emb = arena.gp(pre + "embeddings.word_embeddings.weight")
+        wtab = pre + "embeddings.word_embeddings.weight"
+        if dense_sent:
+            # the table's dense (decoder) gradient is already being averaged: the lookup's rows go to a side table
+            side = getattr(arena, "word_side", None)
+            if side is None or side.shape != arena.shape[wtab]:
+                side = arena.word_side = torch.zeros(arena.shape[wtab], dtype=F32, device=dout.device)
+            g.word_emb = side.data_ptr()
+        else:
+            g.word_emb = arena.gp(wtab)
         g.pos_emb = arena.gp(pre + "embeddings.position_embeddings.weight")
         g.ln_w = arena.gp(pre + "embeddings.LayerNorm.weight")
         g.ln_b = arena.gp(pre + "embeddings.LayerNorm.bias")
@@ -230,7 +239,11 @@ def encoder_backward(enc, arena, st, dout):
     if sync is not None and sync.enabled:
         q0_off = arena.offset[pre + "encoder.layer.0.attention.self.query.weight"]
         wname = pre + "embeddings.word_embeddings.weight"
-        if (st.mode != 2 and arena.offset[wname] == 0 and getattr(sync, "allow_sparse", False)
+        if dense_sent:
+            sync.side_rows(arena.word_side, arena.g(wname), st.keep[0], pad_row=max(int(fam.word_pad), 0))
+            arena.word_rows = None
+            sync.ready(arena.numel[wname], q0_off)           # the table sits at the start of the arena
+        elif (st.mode != 2 and arena.offset[wname] == 0 and getattr(sync, "allow_sparse", False)
                 and not getattr(arena, "word_emb_dense", False)):
             # only token rows of the vocabulary table carry gradient: exchange those rows, not 768 MB of zeros
             w_end = arena.numel[wname]
@@ -331,6 +344,14 @@ def _linear_backward(arena, wname, bname, x, dz, transposed, N, K):
         call("uc2_cast_f32_bf16", dx32.data_ptr(), dx.data_ptr(), dx.numel(), stream())
     if wname.endswith("embeddings.word_embeddings.weight"):
         arena.word_emb_dense = True          # tied decoder: the vocabulary-table gradient is dense this step
+        sync = getattr(arena, "grad_sync", None)
+        if (sync is not None and sync.enabled and getattr(sync, "early_dense", False) and arena.offset[wname] == 0
+                and not getattr(arena, "word_dense_sent", False)):
+            # data parallel: this dense term is complete now, the lookup's rows come at the very end of the backward
+            # pass -> average it under the encoder's backward; embed backward sends its rows separately (side_rows)
+            lo = arena.offset[wname]
+            sync.ready(lo, lo + arena.numel[wname])
+            arena.word_dense_sent = True
     arena.touch(wname, *( [bname] if bname else []))
     return dx
 
@@ -439,9 +460,28 @@ class LayerNormFn(torch.autograd.Function):
         return dx, None, None, None, None
 
 
+_PENDING_COUNTS = []        # (device count, host hint) pairs of MaskedRowsFn calls not yet compared
+
+
+def verify_masked_counts():
+    """The reference's boolean indexing cannot disagree with its own mask; MaskedRowsFn takes the number of set entries as
+    a HOST hint (so the step has no device-to-host sync) and the device scan counts them again.  This compares every
+    pair recorded since the last call (one sync) and raises on a mismatch -- a wrong hint would silently drop rows or
+    append zero rows.  The training loops call it whenever they read their logged losses back."""
+    global _PENDING_COUNTS
+    pending, _PENDING_COUNTS = _PENDING_COUNTS, []
+    if pending:
+        got = torch.stack([c.reshape(()) for c, _ in pending]).cpu().tolist()
+        for g, (_, hint) in zip(got, pending):
+            if int(g) != int(hint):
+                raise RuntimeError(f"masked-row compaction: the batch says {hint} masked positions (n_masked / target rows) "
+                                   f"but the mask holds {g}")
+
+
 class MaskedRowsFn(torch.autograd.Function):
     """hidden[:, :L][mask] in row-major order (model.py:653-657).  `count` is the number of set mask entries
-    (known on the host from the batch, or computed with one sync like the reference's boolean indexing)."""
+    (known on the host from the batch, or computed with one sync like the reference's boolean indexing); the device
+    count is checked against it later (verify_masked_counts), and rows beyond the device count stay zero."""
 
     @staticmethod
     def forward(ctx, hidden, mask, count):
@@ -451,10 +491,13 @@ class MaskedRowsFn(torch.autograd.Function):
         idx = torch.empty(max(count, 1), dtype=torch.int32, device=hidden.device)
         cnt = torch.empty(1, dtype=torch.int32, device=hidden.device)
         call("uc2_mask_scan", m8.data_ptr(), m8.numel(), idx.data_ptr(), cnt.data_ptr(), max(count, 1), stream())
-        out = torch.empty((count, H), dtype=BF16, device=hidden.device)
+        out = torch.zeros((count, H), dtype=BF16, device=hidden.device)
         hidden = hidden.contiguous()
         if count:
             call("uc2_gather_rows", hidden.data_ptr(), idx.data_ptr(), cnt.data_ptr(), L, S, out.data_ptr(), count, stream())
+        _PENDING_COUNTS.append((cnt, count))
+        if len(_PENDING_COUNTS) >= 256:
+            verify_masked_counts()
         ctx.save_for_backward(idx, cnt)
         ctx.meta = (B, S, H, L, count)
         return out

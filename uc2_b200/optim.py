@@ -73,6 +73,11 @@ class AdamW(object):
         arena = _find_arena(p0)
         if arena is self._arena:
             return
+        if self._arena is not None and self.global_step > 0:
+            import warnings
+            warnings.warn("uc2_b200.optim.AdamW: the model's parameter arena was rebuilt (model.to() / .half() / a new "
+                          "device after the first step); exp_avg / exp_avg_sq restart from zero.  Save and reload the "
+                          "optimizer state_dict around such a move to keep the moments.")
         self._arena = arena
         dev = arena.master.device
         by_ptr = {arena.params[n].data_ptr(): n for n in arena.names}
@@ -181,7 +186,8 @@ class AdamW(object):
             else:
                 lz.step_rows(rows, self.global_step, h, sq)
         a.word_rows, a.word_rows_n = None, 0
-        a.word_emb_dense = False             # these three describe the gradient accumulated for ONE optimizer step
+        a.word_emb_dense = False             # these describe the gradient accumulated for ONE optimizer step
+        a.word_dense_sent = False
         self._pending_clip = 0.0
         a.mark_synced()
         return loss
@@ -229,7 +235,11 @@ class AdamW(object):
         return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd):
-        """Accepts the layout above (from this class or from the reference's optim/adamw.py via torch.optim)."""
+        """Accepts the layout above (from this class or from the reference's optim/adamw.py via torch.optim).
+        One incompatibility: the reference's pre-training model registers a `vis_cls.*` head that never receives a
+        gradient (model/model.py:468); this build omits it, so a REFERENCE optimizer checkpoint of that model has larger
+        parameter groups and a shifted index space and is rejected below with the group-size error -- remap it by
+        parameter name first (drop the `vis_cls` slots) if such a checkpoint has to be resumed."""
         self._bind()
         a = self._arena
         if len(sd["param_groups"]) != len(self.param_groups):

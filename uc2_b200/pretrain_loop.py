@@ -58,6 +58,8 @@ class _Deferred(object):
         self.items.append((fn, t.detach().reshape(()).double()))
 
     def flush(self):
+        from .functional import verify_masked_counts
+        verify_masked_counts()          # the same read-back point: the masked-position counts the batches declared
         if not self.items:
             return
         vals = torch.stack([t for _, t in self.items]).tolist()
