@@ -533,7 +533,7 @@ struct TcBwdParams {
 struct TcBwdSmem {
     uint32_t tile_bytes, pt_bytes, off_o, off_ds, off_pd, off_vec, off_bar, total;
     uint32_t tm_s, tm_dp, tm_dv, tm_dk, tm_dq;
-    int nu, nv, nchunk;
+    int nu, nv, nchunk, qb0;       // qb0: queries in block 0 when nv == 2 (block 1 holds the rest)
 };
 // Two shapes of the same pipeline:
 //   SP <= 160  one query block (nv = 1): S^T_u and dP^T_u hold all SP query columns (TMEM [0,SP) and [192,192+SP)), dV_u / dK_u
@@ -546,6 +546,7 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int S, int SP, int blocks = 0) 
     const bool wide = SP > 160 || (blocks == 2 && SP > 128);
     L.nu = S > 128 ? 2 : 1;
     L.nv = wide ? 2 : 1;
+    L.qb0 = SP > 160 ? 128 : 96;                     // (tuning knob blocks == 2 at 128 < SP <= 160: 96 + the rest)
     L.nchunk = wide ? 2 : (SP + 63) >> 6;
     L.tile_bytes = SP * 128u;
     L.pt_bytes = L.nchunk * P_CHUNK_BYTES;
@@ -644,7 +645,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     const uint8_t* gO = gen + L.off_o;
     const uint32_t sDS = base + L.off_ds, sPD = base + L.off_pd;
     const int nv = L.nv;
-    auto nq_of = [&](int v) { return nv == 1 ? SP : (v == 0 ? 128 : SP - 128); };    // queries of block v
+    auto nq_of = [&](int v) { return nv == 1 ? SP : (v == 0 ? L.qb0 : SP - L.qb0); };    // queries of block v
+    const uint32_t qb_bytes = static_cast<uint32_t>(L.qb0) * 128u;                   // Q / dO rows of block 1 start here
 
     if (warp == 0) {
         // ===================================== producer =====================================
@@ -699,9 +701,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                         // rows past SP are the following tiles.  Products of independent accumulators are interleaved.
                         {
                             const uint64_t dk = ptx::smem_desc_sw128(sK + u * 16384u, 16u, 1024u);
-                            const uint64_t dq = ptx::smem_desc_sw128(sQ + v * 16384u, 16u, 1024u);
+                            const uint64_t dq = ptx::smem_desc_sw128(sQ + v * qb_bytes, 16u, 1024u);
                             const uint64_t dv = ptx::smem_desc_sw128(sV + u * 16384u, 16u, 1024u);
-                            const uint64_t dd = ptx::smem_desc_sw128(sdO + v * 16384u, 16u, 1024u);
+                            const uint64_t dd = ptx::smem_desc_sw128(sdO + v * qb_bytes, 16u, 1024u);
 #pragma unroll
                             for (int k = 0; k < HD / 16; ++k) {      // + 32 bytes (2 in the address field) per 16 of head dim
                                 ptx::umma_bf16(tmem_base + L.tm_s, dk + 2u * k, dq + 2u * k, idesc_s, k > 0 ? 1u : 0u);
@@ -721,8 +723,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                         // tiles the block covers (A = the dS^T tile read MN-major: 64-query blocks P_CHUNK_BYTES apart,
                         // 16 key rows per K step; B = K rows of tile u, MN-major): one K step of each per round
                         {
-                            const uint64_t b_do = ptx::smem_desc_sw128(sdO + v * 16384u, 8192u, 1024u);
-                            const uint64_t b_q = ptx::smem_desc_sw128(sQ + v * 16384u, 8192u, 1024u);
+                            const uint64_t b_do = ptx::smem_desc_sw128(sdO + v * qb_bytes, 8192u, 1024u);
+                            const uint64_t b_q = ptx::smem_desc_sw128(sQ + v * qb_bytes, 8192u, 1024u);
                             const uint64_t b_k = ptx::smem_desc_sw128(sK + u * 16384u, 8192u, 1024u);
                             const uint64_t a_dq0 = ptx::smem_desc_sw128(sDS, P_CHUNK_BYTES, 1024u);
                             const uint64_t a_dq1 = ptx::smem_desc_sw128(sDS + 2u * P_CHUNK_BYTES, P_CHUNK_BYTES, 1024u);
@@ -812,7 +814,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 const uint32_t t32 = p.drop.thresh << 16;
                 for (int v = 0; v < nv; ++v) {
                     const uint32_t ph = static_cast<uint32_t>(it * nv + v) & 1u;
-                    const int q_base = v * 128;                                        // first query of the block
+                    const int q_base = v * L.qb0;                                      // first query of the block
                     const int nch = nq_of(v) / 16, per = (nch + NSPLIT - 1) / NSPLIT;   // 16-column chunks per part
                     const int c_begin = min(part * per, nch) * 16, c_end = min((part + 1) * per, nch) * 16;
                     pc.lap(0);
@@ -888,11 +890,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 pc.lap(6);
                 ptx::tc_fence_after();
                 constexpr int WQ = HD / NSPLIT;
+                // dQ tile 0 holds the queries from 0 on, tile 1 those from q1 on (128, or the second query block's start)
+                const int q1 = nv == 2 ? L.qb0 : 128;
+                const int rows0 = nv == 2 ? L.qb0 : (S < 128 ? S : 128);
                 store_cols<WQ>(tmem_base + lane_sel + L.tm_dq + part * WQ,
-                               p.dqkv + (row0 + kr) * QKV_LD + h * HD + part * WQ, kr < S, 0.125f);
-                if (nu == 2 && 128 + q * 32 < S)       // second query tile: rows 128 + (this lane quarter's rows)
+                               p.dqkv + (row0 + kr) * QKV_LD + h * HD + part * WQ, kr < rows0 && kr < S, 0.125f);
+                if (q1 + q * 32 < S)                   // second query tile: rows q1 + (this lane quarter's rows)
                     store_cols<WQ>(tmem_base + lane_sel + L.tm_dq + 64u + part * WQ,
-                                   p.dqkv + (row0 + 128 + kr) * QKV_LD + h * HD + part * WQ, 128 + kr < S, 0.125f);
+                                   p.dqkv + (row0 + q1 + kr) * QKV_LD + h * HD + part * WQ, q1 + kr < S, 0.125f);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(dq_empty);
