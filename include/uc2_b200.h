@@ -114,6 +114,13 @@ UC2_API int uc2_ce_bwd_inplace_bf16(void* logits_bf16, long long ld, long long r
  * it lets NCCL use, so that neither side waits for an SM the other holds.  Returns the previous value. */
 UC2_API int uc2_reserve_sms(int n);
 
+/* Tile order of the persistent GEMM workers.  0 (default): fixed round-robin, no per-launch overhead.  1: tiles are drawn
+ * from a device counter, so a worker whose SM was busy when the grid started (a NCCL kernel of the overlapped gradient
+ * exchange holds it) finds the work done and leaves instead of running its whole fixed share late.  Data-parallel
+ * training (world size > 1) switches it on; UC2_GEMM_SCHED=dynamic|static in the environment sets the initial value.
+ * Same results either way (split-K accumulation order aside).  Returns the previous value. */
+UC2_API int uc2_gemm_sched_dynamic(int on);
+
 /* ---------------------------------------------------------------------------------------------
  * Embeddings fused with the gather_index pack.
  * Replaces {VLXLMR,Uniter}TextEmbeddings.forward (model/model.py:304-335, 987-1001),

@@ -137,7 +137,7 @@ _SIGS = {
     "uc2_adamw_lazy_catchup": [C.POINTER(LazyTable), P, LL, I, P],
     "uc2_grad_sqnorm_rows": [C.POINTER(LazyTable), P, LL, I, P, P],
 }
-EXPORTS = sorted(list(_SIGS) + ["uc2_last_error", "uc2_version", "uc2_launch_count", "uc2_attention_tc_enable", "uc2_reserve_sms",
+EXPORTS = sorted(list(_SIGS) + ["uc2_last_error", "uc2_version", "uc2_launch_count", "uc2_attention_tc_enable", "uc2_reserve_sms", "uc2_gemm_sched_dynamic",
                                 "uc2_encoder_bwd_workspace_bytes", "uc2_encoder_fwd_workspace_bytes"])
 
 

@@ -44,6 +44,7 @@ struct ProfScope {
 };
 int require_sm100();
 bool pdl_enabled();      // programmatic dependent launch (off with UC2_NO_PDL=1)
+bool gemm_sched_dynamic();   // persistent GEMM workers draw tiles from a counter (uc2_gemm_sched_dynamic)
 bool attn_tc_enabled();  // tcgen05 attention kernels (attention_tc.cu) in use; UC2_ATTN_TCGEN05=0 switches them off
 inline bool attn_tc_bwd_serves(int S) { return (S + 15) / 16 * 16 <= 256; }   // shapes uc2_attention_bwd_tc takes
 

@@ -44,6 +44,17 @@ __host__ __device__ constexpr int gemm_threads(int mode) { return 64 + 32 * epi_
 __host__ __device__ constexpr bool tma_out(int mode) { return mode == 3 || mode == 8; }
 constexpr int OUT_BOX_BYTES = 32 * 32 * 4;
 
+// Dynamic tile scheduler.  The persistent workers (CTAs, or CTA pairs) of a launch draw their tiles from one global
+// counter instead of the fixed round-robin  t = worker, worker + n, ...  so that a worker which becomes resident late
+// -- its SM was held by another kernel, typically a NCCL collective of the overlapped gradient exchange -- finds the
+// work already done and leaves, instead of the whole GEMM waiting for a late starter to walk through its full share.
+// One thread per worker (the TMA producer of the leader CTA) draws the index and hands it to the other roles of
+// both CTAs through a small ring in shared memory: sched_full[slot] (count 1, in every CTA) says the slot holds tile
+// number `it`, sched_empty[slot] (in the leader, one arrive per consumer of both CTAs) says everybody has read it.
+constexpr int SCHED_R = 4;           // ring slots: the producer runs at most a tile or two ahead of the epilogue
+constexpr int BAR_BYTES = 384;       // mbarriers + TMEM pointer + scheduler ring at the end of shared memory
+constexpr int SCHED_SLOTS = 1024;    // (counter, finished workers) pairs handed out to launches in turn
+
 template <int BLOCK_N, int CTAS, int MODE = 0>
 struct Cfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -51,11 +62,11 @@ struct Cfg {
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGING_BYTES = tma_out(MODE) ? epi_warps(MODE) * OUT_BOX_BYTES : 0;
-    static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - 256 - STAGING_BYTES) / STAGE_BYTES;
+    static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;   // two accumulator buffers; 128/256/512: power of two
     // layout: [stages][staging boxes (1024-byte aligned: STAGE_BYTES is a multiple of 1024)][barriers]
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 256;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
 };
 
 struct GemmParams {
@@ -78,6 +89,9 @@ struct GemmParams {
     int tail_start, tail_split;
     // MODE 9: cross-entropy statistics per (row, 32-column chunk), see uc2_gemm_args
     float2* ce_stats; long long ce_ld; const long long* ce_labels; float* ce_tgt;
+    // dynamic tile scheduler: sched[0] = next tile, sched[1] = workers that have drawn their last (invalid) tile; both
+    // zero at launch, the last worker to finish zeroes them again for the launch that gets this pair next
+    int* sched;
 };
 
 struct TileCoord { int m_blk, n0, width, split; };
@@ -405,12 +419,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES;
-    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr,
+    // sched_full[SCHED_R], sched_empty[SCHED_R], then the ring of tile numbers (4 B each)
+    static_assert(8 * (2 * C::STAGES + 5 + 2 * SCHED_R) + 4 * SCHED_R <= BAR_BYTES, "barrier region too small");
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::STAGES + 4);
+    auto sfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 5 + s); };
+    auto sempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 5 + SCHED_R + s); };
+    auto ring_slot = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 5 + 2 * SCHED_R) + 4u * s; };
     volatile uint32_t* tmem_ptr_gen =
         reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES +
                                              8 * (2 * C::STAGES + 4));
@@ -420,6 +439,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t cta_rank = CTAS == 2 ? ptx::cluster_ctarank() : 0u;
     const int unit = CTAS == 2 ? (blockIdx.x >> 1) : blockIdx.x;          // persistent worker (CTA or CTA pair)
     const int num_units = CTAS == 2 ? (gridDim.x >> 1) : gridDim.x;
+    // p.sched == nullptr: fixed round-robin tiles (t = unit, unit + num_units, ...); otherwise drawn from a counter.
+    // The first number is requested before anything else so that the atomic's round trip runs under the prologue.
+    const bool dyn = p.sched != nullptr;
+    int first_tile = unit;
+    if (dyn && threadIdx.x == 0 && cta_rank == 0) first_tile = atomicAdd(p.sched, 1);
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -432,6 +456,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull_bar(a), 1);
             ptx::mbar_init(tempty_bar(a), epi_warps(MODE) * CTAS);   // one arrive per epilogue warp of every CTA
+        }
+        for (int s = 0; s < SCHED_R; ++s) {
+            ptx::mbar_init(sfull_bar(s), 1);
+            // readers of a tile number: the MMA thread and the leader's epilogue warps, plus (pairs) the peer's
+            // producer and epilogue warps; the leader's producer is the writer
+            ptx::mbar_init(sempty_bar(s), (1 + epi_warps(MODE)) * CTAS);
         }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -450,28 +480,90 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
-    // everything above (barriers, TMEM, descriptor prefetch) may have run under the previous kernel's tail
-    griddep_sync();
 
     const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
     const int total_tiles = p.tail_split > 1 ? p.tail_start + (tiles_mn - p.tail_start) * p.tail_split
                                              : tiles_mn * p.split_k;
+
+    // ---- tile scheduler (see SCHED_R) ----
+    // writer side: the leader's producer thread.  The counter pair belongs to this launch alone, so drawing from it
+    // does not have to wait for the previous kernel of the stream.
+    auto sched_account = [&](int t) {
+        if (t >= total_tiles && atomicAdd(p.sched + 1, 1) == num_units - 1) {
+            // every worker has drawn its last number: leave the pair zeroed for the launch that gets it next
+            atomicExch(p.sched, 0);
+            atomicExch(p.sched + 1, 0);
+        }
+    };
+    auto sched_publish = [&](int it, int t) {
+        const int slot = it % SCHED_R;
+        const uint32_t parity = (((uint32_t)it / SCHED_R) & 1u) ^ 1u;
+        if (CTAS == 2) ptx::mbar_wait_cluster(sempty_bar(slot), parity);
+        else ptx::mbar_wait(sempty_bar(slot), parity);
+        ptx::st_shared_b32(ring_slot(slot), (uint32_t)t);
+        ptx::mbar_arrive(sfull_bar(slot));
+        if (CTAS == 2) {
+            ptx::st_shared_cluster_b32(ptx::map_to_cta(ring_slot(slot), 1), (uint32_t)t);
+            ptx::mbar_arrive_remote(ptx::map_to_cta(sfull_bar(slot), 1));       // release at cluster scope
+        }
+    };
+    // reader side: waits for tile number `it` of this worker and returns it (>= total_tiles: no more work)
+    auto sched_read = [&](int it) -> int {
+        if (!dyn) return unit + it * num_units;
+        const int slot = it % SCHED_R;
+        const uint32_t parity = ((uint32_t)it / SCHED_R) & 1u;
+        if (CTAS == 2) ptx::mbar_wait_cluster(sfull_bar(slot), parity);
+        else ptx::mbar_wait(sfull_bar(slot), parity);
+        return (int)ptx::ld_shared_b32(ring_slot(slot));
+    };
+    // ... and gives the slot back.  RELAXED: for the epilogue warps, whose release would wait for their global stores
+    // in flight; the value has been consumed (shuffled) by then.  Otherwise a release arrive.
+    auto sched_done = [&](int it, bool relaxed) {
+        if (!dyn) return;
+        const int slot = it % SCHED_R;
+        if (CTAS == 2) {
+            const uint32_t b = ptx::map_to_cta(sempty_bar(slot), 0);
+            if (relaxed) ptx::mbar_arrive_remote_relaxed(b);
+            else ptx::mbar_arrive_remote(b);
+        } else {
+            ptx::mbar_arrive(sempty_bar(slot));
+        }
+    };
+    if (dyn && threadIdx.x == 0 && cta_rank == 0) {
+        sched_account(first_tile);
+        sched_publish(0, first_tile);
+    }
+    // everything above (barriers, TMEM, descriptor prefetch, the first tile number) may have run under the
+    // previous kernel's tail
+    griddep_sync();
 
     if (warp_idx == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = unit; t < total_tiles; t += num_units) {
+            const bool sched_writer = dyn && cta_rank == 0;
+            int t = first_tile;
+            for (int it = 0;; ++it) {
+                if (!sched_writer) {
+                    t = sched_read(it);
+                    sched_done(it, false);
+                }
+                if (t >= total_tiles) break;
+                int t_next = 0;
                 const TileCoord tc = decode_tile<BLOCK_N>(p, t, tiles_mn);
                 const int kb0 = tc.split * p.k_blocks_per_split;
                 const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+                // the next tile number is requested while the last k blocks of this tile are still being issued and
+                // looked at only after the last of them: the atomic's round trip never stalls the loads
+                const int kb_draw = max(kb0, kb1 - 8);
                 const int m0 = (tc.m_blk * CTAS + (int)cta_rank) * BLOCK_M;
                 const int b_rows = tc.width / CTAS;                       // B rows (n) this CTA stages for the tile
                 const int n0 = tc.n0 + (int)cta_rank * b_rows;
                 const bool narrow = tc.width != BLOCK_N;
                 const uint32_t stage_tx = (C::A_BYTES + b_rows * BLOCK_K * 2) * CTAS;
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    if (sched_writer && kb == kb_draw) t_next = atomicAdd(p.sched, 1);
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                     const uint32_t sb = sa + C::A_BYTES;
@@ -497,6 +589,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
+                if (sched_writer) {
+                    sched_account(t_next);
+                    sched_publish(it + 1, t_next);
+                    t = t_next;
+                }
             }
         }
     } else if (warp_idx == 1) {
@@ -511,7 +608,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = unit; t < total_tiles; t += num_units) {
+            int t = sched_read(0);
+            sched_done(0, true);
+            for (int it = 0; t < total_tiles; ++it) {
+                int t_next = 0;
                 const TileCoord tc = decode_tile<BLOCK_N>(p, t, tiles_mn);
                 const int kb0 = tc.split * p.k_blocks_per_split;
                 const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
@@ -522,6 +622,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    if (kb == kb1 - 1) {
+                        // the next tile number (published long ago: the producer is stages ahead) is fetched while the
+                        // MMAs of the previous k block are still queued, not between two tiles
+                        t_next = sched_read(it + 1);
+                        sched_done(it + 1, true);
+                    }
                     ptx::mbar_wait(full_bar(stage), phase);
                     ptx::tc_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -543,6 +649,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (CTAS == 2) ptx::umma_commit_pair(tfull_bar(acc));
                 else ptx::umma_commit(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                t = t_next;
             }
         }
     } else {
@@ -553,7 +660,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                       : (p.residual ? (p.res_f32 ? 2 : 1) : (p.act == UC2_ACT_DGELU ? 1 : 0));
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = unit; t < total_tiles; t += num_units) {
+        for (int it = 0;; ++it) {
+            const int t = __shfl_sync(0xffffffffu, sched_read(it), 0);
+            if (lane == 0) sched_done(it, true);
+            if (t >= total_tiles) break;
             const TileCoord tc = decode_tile<BLOCK_N>(p, t, tiles_mn);
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
             const long long grow = (long long)(tc.m_blk * CTAS + (int)cta_rank) * BLOCK_M + q * 32 + lane;
@@ -605,6 +715,27 @@ int make_tmap_out_f32(CUtensorMap* m, const void* base, long long rows, long lon
     UC2_REQUIRE(r == CUDA_SUCCESS, UC2_ERR_CUDA, "cuTensorMapEncodeTiled(out f32) failed (%d): rows=%lld cols=%lld ld=%lld",
                 (int)r, rows, cols, ld);
     return UC2_OK;
+}
+
+// The (counter, finished workers) pair of the next launch: SCHED_SLOTS pairs per device, zeroed once, handed out in
+// turn; a launch leaves its pair zeroed (sched_draw), and a pair comes around again SCHED_SLOTS launches later.
+int* next_sched_pair() {
+    static std::mutex mu;
+    static int* base[64] = {};
+    static unsigned next[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!base[dev]) {
+        int* q = nullptr;
+        if (cudaMalloc(&q, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+        if (cudaMemset(q, 0, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+            cudaFree(q);
+            return nullptr;
+        }
+        base[dev] = q;
+    }
+    return base[dev] + 2 * (next[dev]++ % SCHED_SLOTS);
 }
 
 // How many persistent workers (CTAs, or CTA pairs) the device can hold for one kernel instantiation.
@@ -683,6 +814,11 @@ int launch(const uc2_gemm_args& a, const GemmParams& p_in, cudaStream_t stream) 
     }
     const int total = p.tail_split > 1 ? p.tail_start + (tiles_mn - p.tail_start) * p.tail_split : tiles_mn * p.split_k;
     const int workers = total < slots ? total : slots;
+    p.sched = nullptr;
+    if (gemm_sched_dynamic() && total > workers) {
+        p.sched = next_sched_pair();
+        UC2_REQUIRE(p.sched != nullptr, UC2_ERR_CUDA, "gemm: could not allocate the tile scheduler counters");
+    }
     {
         ProfScope prof(stream, 0, 2.0 * a.M * a.N * a.K);
         launch_pdl(kern, dim3(CTAS * workers), dim3(gemm_threads(MODE)), C::SMEM_BYTES, stream, CTAS, ta, tb, tb_tail, tout, p);

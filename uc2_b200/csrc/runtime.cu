@@ -97,6 +97,18 @@ int make_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, 
     return UC2_OK;
 }
 
+// dynamic tile scheduler of the persistent GEMM (gemm_tcgen05.cu: SCHED_R)
+static std::atomic<int> g_gemm_dynamic{-1};
+bool gemm_sched_dynamic() {
+    int v = g_gemm_dynamic.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("UC2_GEMM_SCHED");
+        v = (e && e[0] == 'd') ? 1 : 0;
+        g_gemm_dynamic.store(v, std::memory_order_relaxed);
+    }
+    return v == 1;
+}
+
 bool pdl_enabled() {
     static int on = -1;
     if (on < 0) {
@@ -174,6 +186,12 @@ extern "C" UC2_API int uc2_profile_collect(double* ms_by_kind, double* work_by_k
 extern "C" UC2_API const char* uc2_last_error(void) { return uc2::g_err; }
 extern "C" UC2_API int uc2_version(void) { return 100; }
 extern "C" UC2_API long long uc2_launch_count(void) { return uc2::g_launches.load(); }
+
+extern "C" UC2_API int uc2_gemm_sched_dynamic(int on) {
+    const int prev = uc2::gemm_sched_dynamic() ? 1 : 0;
+    uc2::g_gemm_dynamic.store(on ? 1 : 0, std::memory_order_relaxed);
+    return prev;
+}
 
 extern "C" UC2_API int uc2_reserve_sms(int n) {
     const int prev = uc2::g_reserved_sms.load(std::memory_order_relaxed);

@@ -105,6 +105,11 @@ class GradSync(object):
                                 # backward pass (no NCCL kernel holds SMs while the persistent GEMMs run)
         self.early_dense = True # tied-decoder steps: exchange the dense table gradient as soon as the decoder's wgrad is
                                 # written, the embedding lookup's rows separately at the end (side_rows)
+        if flat_grad.is_cuda and size() > 1 and "UC2_GEMM_SCHED" not in os.environ:
+            # NCCL's kernels will hold SMs while the persistent GEMMs run: let their workers draw tiles from a counter
+            # so that a worker that starts late leaves at once (include/uc2_b200.h: uc2_gemm_sched_dynamic)
+            from ._lib import lib
+            lib().uc2_gemm_sched_dynamic(1)
 
     def _submit(self, s, e):
         if self.comm_dtype is None:
