@@ -450,6 +450,11 @@ def run_training(args, workload, rank, world, steps, warmup, with_cpu, with_stor
                         grad_comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else None,
                         grad_overlap=not args.no_grad_overlap)
 
+    if os.environ.get("UC2_BENCH_NO_EXCHANGE") == "1":
+        # debug only (the replicas diverge): no gradient exchange at all, to separate what N > 1 costs through the
+        # exchange from what it costs through N processes sharing one host
+        step_fn._ensure_sync = lambda: model._arena()
+
     host = [(t, pin(b)) for t, b in host_batches(workload, 1000 + rank)]
     resident = [(t, UB.to_device(b, dev)) for t, b in host]
     torch.cuda.synchronize()

@@ -244,6 +244,80 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return fmaf(x * 0.3989422804014327f, g.e, Phi);
 }
 
+// ---- packed fp32 pairs: Blackwell executes fma / mul / add on two fp32 values per lane in one instruction (FFMA2,
+// FMUL2, FADD2; each half is rounded exactly like the scalar instruction).  The GELU epilogues of the GEMM are bound
+// by the FP32 pipe, not by the tensor pipe they are meant to hide under; in pairs they cost half the pipe time.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ void up2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 splat2(float a) { return pk2(a, a); }
+__device__ __forceinline__ uint32_t pack_bf16x2(f32x2 v) {
+    float a, b;
+    up2(v, a, b);
+    return pack_bf16(a, b);
+}
+
+// gelu_terms() on a pair, the same operations in the same order (bit-identical halves).  nax = -|x|: its product
+// with -k is the scalar form's k |x|, and it is the multiplier of gelu's last fma.
+struct GeluTerms2 { f32x2 h, e, nax; };
+__device__ __forceinline__ GeluTerms2 gelu_terms2(f32x2 x) {
+    float x0, x1;
+    up2(x, x0, x1);
+    GeluTerms2 g;
+    g.nax = pk2(-fabsf(x0), -fabsf(x1));
+    const f32x2 d = fma2(g.nax, splat2(-(0.47047f * 0.70710678118654752f)), splat2(1.0f));
+    float d0, d1;
+    up2(d, d0, d1);
+    const f32x2 t = pk2(fast_rcp(d0), fast_rcp(d1));
+    f32x2 pl = fma2(splat2(0.5f * 0.7478556f), t, splat2(0.5f * -0.0958798f));
+    pl = fma2(pl, t, splat2(0.5f * 0.3480242f));
+    const f32x2 xx = mul2(mul2(x, x), splat2(-0.5f * 1.4426950408889634f));
+    float q0, q1;
+    up2(xx, q0, q1);
+    g.e = pk2(fast_ex2(q0), fast_ex2(q1));
+    g.h = mul2(mul2(pl, t), g.e);
+    return g;
+}
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
+    const GeluTerms2 g = gelu_terms2(x);
+    float x0, x1;
+    up2(x, x0, x1);
+    return fma2(g.nax, g.h, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+__device__ __forceinline__ f32x2 gelu_erf_grad2(f32x2 x) {
+    const GeluTerms2 g = gelu_terms2(x);
+    const f32x2 s = fma2(g.h, splat2(-1.0f), splat2(0.5f));          // 0.5 - h, one rounding like the scalar form
+    float x0, x1, s0, s1;
+    up2(x, x0, x1);
+    up2(s, s0, s1);
+    const f32x2 Phi = add2(splat2(0.5f), pk2(copysignf(s0, x0), copysignf(s1, x1)));
+    return fma2(mul2(x, splat2(0.3989422804014327f)), g.e, Phi);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace uc2

@@ -210,8 +210,8 @@ __device__ __forceinline__ void ln_bwd_row(const float* x, float* dy, const floa
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         const float xh = (x[i] - mean) * rstd;
-        atomicAdd(acc_dgamma + i * 32 + lane, dy[i] * xh);      // an accumulator set is shared by EMB_BWD_SHARE warps
-        atomicAdd(acc_dbeta + i * 32 + lane, dy[i]);
+        acc_dgamma[i * 32 + lane] += dy[i] * xh;
+        acc_dbeta[i * 32 + lane] += dy[i];
         const float gd = g[i] * dy[i];
         s1 += gd;
         s2 += gd * xh;
@@ -240,17 +240,15 @@ __device__ __forceinline__ void red_row(float* dst, int lane, const float* v) {
 //  0 ln_w 1 ln_b 2 type0 | 3 fin_w 4 fin_b 5 type1 6 img_w 7 img_b 8 posln_w 9 posln_b 10 pos_b 11..17 pos_w[:,d]
 constexpr int N_ACC = 18;
 
-// 4 accumulator sets x 18 x 768 fp32 = 216 KB of shared memory, each shared by 2 warps through shared-memory atomics
-// (one warp per set left the SM with four warps of long dependent LayerNorm-backward chains: latency bound)
-constexpr int EMB_BWD_SETS = 4, EMB_BWD_SHARE = 2, EMB_BWD_WARPS = EMB_BWD_SETS * EMB_BWD_SHARE;
+constexpr int EMB_BWD_WARPS = 4;      // 4 private accumulator sets x 18 x 768 fp32 = 216 KB of shared memory
 
 __global__ void __launch_bounds__(EMB_BWD_WARPS * 32)
 embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const EmbedGrads g) {
     extern __shared__ float acc_all[];
-    for (int i = threadIdx.x; i < EMB_BWD_SETS * N_ACC * HID; i += blockDim.x) acc_all[i] = 0.f;
+    for (int i = threadIdx.x; i < EMB_BWD_WARPS * N_ACC * HID; i += blockDim.x) acc_all[i] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    float* acc = acc_all + ((threadIdx.x >> 5) % EMB_BWD_SETS) * N_ACC * HID;     // the accumulator set of this warp
+    float* acc = acc_all + (threadIdx.x >> 5) * N_ACC * HID;     // this warp's private accumulators
     const long long nrows = (long long)p.B * p.S;
     for (long long row = (long long)blockIdx.x * EMB_BWD_WARPS + (threadIdx.x >> 5); row < nrows;
          row += (long long)gridDim.x * EMB_BWD_WARPS) {
@@ -270,7 +268,7 @@ embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const 
             text_presum(p, id, pos, lane, x);
             ln_bwd_row(x, dy, p.ln_w, lane, p.eps, acc + 0 * HID, acc + 1 * HID);
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) atomicAdd(acc + 2 * HID + i * 32 + lane, dy[i]);
+            for (int i = 0; i < VPL; ++i) acc[2 * HID + i * 32 + lane] += dy[i];
             // nn.Embedding(padding_idx) never receives gradient on its padding row
             if (id != p.word_pad_id) red_row(g.word_emb + id * HID, lane, dy);
             if (pos != p.pos_pad_id) red_row(g.pos_emb + (long long)pos * HID, lane, dy);
@@ -294,7 +292,7 @@ embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const 
             // final LN
             ln_bwd_row(x, dy, p.fin_ln_w, lane, p.eps, acc + 3 * HID, acc + 4 * HID);
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) atomicAdd(acc + 5 * HID + i * 32 + lane, dy[i]);
+            for (int i = 0; i < VPL; ++i) acc[5 * HID + i * 32 + lane] += dy[i];
             // branch: img LN
             float d1[VPL];
 #pragma unroll
@@ -305,9 +303,9 @@ embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const 
             ln_bwd_row(q, dy, p.pos_ln_w, lane, p.eps, acc + 8 * HID, acc + 9 * HID);
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
-                atomicAdd(acc + 10 * HID + i * 32 + lane, dy[i]);
+                acc[10 * HID + i * 32 + lane] += dy[i];
 #pragma unroll
-                for (int d = 0; d < 7; ++d) atomicAdd(acc + (11 + d) * HID + i * 32 + lane, dy[i] * f7[d]);
+                for (int d = 0; d < 7; ++d) acc[(11 + d) * HID + i * 32 + lane] += dy[i] * f7[d];
             }
         }
     }
@@ -317,7 +315,7 @@ embed_pack_bwd_kernel(const EmbedParams p, const bf16* __restrict__ dout, const 
         auto flush = [&](int k, float* dst) {
             float v = 0.f;
 #pragma unroll
-            for (int w = 0; w < EMB_BWD_SETS; ++w) v += acc_all[(w * N_ACC + k) * HID + sl];
+            for (int w = 0; w < EMB_BWD_WARPS; ++w) v += acc_all[(w * N_ACC + k) * HID + sl];
             if (v != 0.f) atomicAdd(dst, v);
         };
         if (p.mode != 2) {
@@ -458,7 +456,7 @@ extern "C" UC2_API int uc2_embed_pack_bwd(const uc2_embed_args* a, const void* d
                                  g.fin_ln_w && g.fin_ln_b && g.dy_img && g.type_emb, UC2_ERR_ARG,
                                  "embed_pack_bwd: image grads missing");
     static bool attr_set = false;
-    const int smem = EMB_BWD_SETS * N_ACC * HID * (int)sizeof(float);
+    const int smem = EMB_BWD_WARPS * N_ACC * HID * (int)sizeof(float);
     if (!attr_set) {
         UC2_CUDA(cudaFuncSetAttribute(embed_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;

@@ -211,6 +211,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
     float ce_m = 0.f, ce_s = 0.f;
     const int ce_t = (MODE == 9 && row_ok) ? static_cast<int>(p.ce_labels[grow]) : -1;
     uint32_t pf[EX == 0 ? 1 : G * W];
+    // MODE 1: the 16 bias values of the NEXT 16-column slice are requested while the current slice goes through the
+    // GELU (the first slice of a tile: before the wait for the accumulator) -- the shared-memory carve-out leaves
+    // almost no L1, so a bias load issued at its point of use is a trip to L2 with the warp stalled on it
+    float4 bq[MODE == 1 ? 4 : 1];
+    auto bias_ok = [&](int c) { return p.vec_ok && c * EPI_COLS < ncols && ncol0 + (c + 1) * EPI_COLS <= p.N; };
+    auto bias_fetch = [&](int c, int h) {
+#pragma unroll
+        for (int j = 0; j < (MODE == 1 ? 4 : 1); ++j)
+            bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + c * EPI_COLS + h * 16) + j);
+    };
     const bf16* exb = F::residual(p) ? p.residual : p.aux;
     const long long ld_ex = F::residual(p) ? p.ld_res : p.ld_aux;
 #pragma unroll 1
@@ -229,6 +239,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
             }
         }
         if (g0 == 0) {
+            if (MODE == 1 && row_ok && bias_ok(half)) bias_fetch(half, 0);
             ptx::mbar_wait(tfull, tfull_phase);
             ptx::tc_fence_after();
         }
@@ -259,7 +270,39 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tacc
                 // the TMA-store path needs the whole warp (rows beyond M are clipped by the tensor map)
                 if (!row_ok && !tma_out(MODE)) continue;
                 const uint32_t* ex = pf + ii * W + h * (W / 2);
-                if (p.vec_ok && ncol0 + (c + 1) * EPI_COLS <= p.N) {
+                if ((MODE == 1 || MODE == 2) && p.vec_ok && ncol0 + (c + 1) * EPI_COLS <= p.N) {
+                    // the two GELU epilogues on packed fp32 pairs (common.cuh: FFMA2 / FMUL2 / FADD2), same values
+                    f32x2 w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[j] = pk2u(r[2 * j], r[2 * j + 1]);
+                    if (MODE == 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            w[2 * j] = add2(w[2 * j], pk2(bq[j].x, bq[j].y));
+                            w[2 * j + 1] = add2(w[2 * j + 1], pk2(bq[j].z, bq[j].w));
+                        }
+                        if (h == 0) {
+                            bias_fetch(c, 1);
+                        } else {
+                            const int cn = CG * (g0 + ii + 1) + half;
+                            if (g0 + ii + 1 < MY && bias_ok(cn)) bias_fetch(cn, 0);
+                        }
+                        ptx::stg256(p.out_pre + grow * p.ld_pre + col0, pack_bf16x2(w[0]), pack_bf16x2(w[1]),
+                                    pack_bf16x2(w[2]), pack_bf16x2(w[3]), pack_bf16x2(w[4]), pack_bf16x2(w[5]),
+                                    pack_bf16x2(w[6]), pack_bf16x2(w[7]));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w[j] = gelu_erf2(w[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 u = unpack_bf16(ex[j]);
+                            w[j] = mul2(w[j], gelu_erf_grad2(pk2(u.x, u.y)));
+                        }
+                    }
+                    ptx::stg256(p.out_bf16 + grow * p.ld_out + col0, pack_bf16x2(w[0]), pack_bf16x2(w[1]),
+                                pack_bf16x2(w[2]), pack_bf16x2(w[3]), pack_bf16x2(w[4]), pack_bf16x2(w[5]),
+                                pack_bf16x2(w[6]), pack_bf16x2(w[7]));
+                } else if (p.vec_ok && ncol0 + (c + 1) * EPI_COLS <= p.N) {
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
