@@ -120,6 +120,9 @@ UC2_API int uc2_reserve_sms(int n);
  * training (world size > 1) switches it on; UC2_GEMM_SCHED=dynamic|static in the environment sets the initial value.
  * Same results either way (split-K accumulation order aside).  Returns the previous value. */
 UC2_API int uc2_gemm_sched_dynamic(int on);
+/* Test support: n_ctas CTAs that each hold a whole SM (200 KB of shared memory) for `cycles` clocks on `stream` -- a
+ * stand-in for a communication kernel that keeps SMs from the persistent kernels. */
+UC2_API int uc2_debug_occupy_sms(int n_ctas, long long cycles, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Embeddings fused with the gather_index pack.

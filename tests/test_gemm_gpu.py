@@ -199,3 +199,47 @@ def test_bench_sized_token_dim_tail_split(N, K):
     _check(out, ref, 2e-5, "fp32 out")
     _check(ob, ref, 1e-2, "bf16 out")
     assert torch.equal(out[-300:].bfloat16(), ob[-300:])
+
+
+@pytest.mark.parametrize("held_sms", [0, 36, 100])
+def test_dynamic_tile_order_with_sms_held_by_another_kernel(held_sms):
+    """uc2_gemm_sched_dynamic: workers draw tiles from a device counter.  With SMs held by another kernel (what a NCCL
+    collective of the overlapped gradient exchange does) some workers become resident only after the counter has run
+    out: they must leave at once, every tile must still be computed exactly once, and the counter pair must be left
+    zeroed for its next user.  Same bits as the fixed tile order (no split-K here)."""
+    from uc2_b200 import _lib
+    L = _lib.lib()
+    M, N, K = 10240, 2304, 768
+    a = _rand((M, K), 40).bfloat16()
+    b = _rand((N, K), 41, 0.05).bfloat16()
+    bias = _rand((N,), 42)
+    aux = _rand((M, N), 43).bfloat16()
+    ref = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ref_g = torch.empty_like(ref)
+    dw_ref = torch.zeros(N, K, dtype=torch.float32, device="cuda")
+    prev = L.uc2_gemm_sched_dynamic(0)
+    try:
+        _lib.gemm(a, b, M, N, K, bias=bias, out_bf16=ref)
+        _lib.gemm(a, b, M, N, K, bias=bias, act=_lib.ACT_GELU, out_bf16=ref_g, out_pre=torch.empty_like(ref))
+        _lib.gemm(ref, a, N, K, M, a_mn=True, b_mn=True, out_f32=dw_ref, accumulate=True, split_k=0)
+        torch.cuda.synchronize()
+        L.uc2_gemm_sched_dynamic(1)
+        side = torch.cuda.Stream()
+        outs = [torch.empty_like(ref) for _ in range(6)]
+        outs_g = [torch.empty_like(ref) for _ in range(6)]
+        pre = torch.empty_like(ref)
+        dw = torch.zeros_like(dw_ref)
+        if held_sms:
+            # ~3 ms at 1.9 GHz: longer than the 13 GEMMs below, so late workers exist in every one of them
+            assert L.uc2_debug_occupy_sms(held_sms, 6_000_000, side.cuda_stream) == 0
+        for o, og in zip(outs, outs_g):
+            _lib.gemm(a, b, M, N, K, bias=bias, out_bf16=o)
+            _lib.gemm(a, b, M, N, K, bias=bias, act=_lib.ACT_GELU, out_bf16=og, out_pre=pre)
+        _lib.gemm(ref, a, N, K, M, a_mn=True, b_mn=True, out_f32=dw, accumulate=True, split_k=0)
+        torch.cuda.synchronize()
+    finally:
+        L.uc2_gemm_sched_dynamic(prev)
+    for o, og in zip(outs, outs_g):
+        assert torch.equal(o, ref)
+        assert torch.equal(og, ref_g)
+    _check(dw, dw_ref, 1e-5, "split-K wgrad under the dynamic tile order")

@@ -137,7 +137,7 @@ _SIGS = {
     "uc2_adamw_lazy_catchup": [C.POINTER(LazyTable), P, LL, I, P],
     "uc2_grad_sqnorm_rows": [C.POINTER(LazyTable), P, LL, I, P, P],
 }
-EXPORTS = sorted(list(_SIGS) + ["uc2_last_error", "uc2_version", "uc2_launch_count", "uc2_attention_tc_enable", "uc2_reserve_sms", "uc2_gemm_sched_dynamic",
+EXPORTS = sorted(list(_SIGS) + ["uc2_last_error", "uc2_version", "uc2_launch_count", "uc2_attention_tc_enable", "uc2_reserve_sms", "uc2_gemm_sched_dynamic", "uc2_debug_occupy_sms",
                                 "uc2_encoder_bwd_workspace_bytes", "uc2_encoder_fwd_workspace_bytes"])
 
 
@@ -157,6 +157,12 @@ def lib():
         L.uc2_encoder_fwd_workspace_bytes.argtypes = [I, I]
         L.uc2_attention_tc_enable.restype = I
         L.uc2_attention_tc_enable.argtypes = [I]
+        L.uc2_gemm_sched_dynamic.restype = I
+        L.uc2_gemm_sched_dynamic.argtypes = [I]
+        L.uc2_reserve_sms.restype = I
+        L.uc2_reserve_sms.argtypes = [I]
+        L.uc2_debug_occupy_sms.restype = I
+        L.uc2_debug_occupy_sms.argtypes = [I, LL, P]
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.argtypes = sig

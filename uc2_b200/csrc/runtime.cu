@@ -187,6 +187,32 @@ extern "C" UC2_API const char* uc2_last_error(void) { return uc2::g_err; }
 extern "C" UC2_API int uc2_version(void) { return 100; }
 extern "C" UC2_API long long uc2_launch_count(void) { return uc2::g_launches.load(); }
 
+// Test support: n_ctas CTAs that each take a whole SM (200 KB of shared memory) and spin for `cycles` clocks -- what a
+// communication kernel holding SMs looks like to the persistent kernels (tests/test_gemm_gpu.py).
+namespace uc2 {
+__global__ void __launch_bounds__(128) occupy_sms_kernel(long long cycles, unsigned int* sink) {
+    extern __shared__ unsigned int occ_smem[];
+    occ_smem[threadIdx.x] = threadIdx.x;
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) __nanosleep(200);
+    if (sink && occ_smem[threadIdx.x] == 0xFFFFFFFFu) *sink = 1u;
+}
+}  // namespace uc2
+
+extern "C" UC2_API int uc2_debug_occupy_sms(int n_ctas, long long cycles, void* stream) {
+    using namespace uc2;
+    UC2_REQUIRE(n_ctas > 0 && n_ctas <= 1024 && cycles >= 0 && cycles <= 4000000000LL, UC2_ERR_ARG,
+                "debug_occupy_sms: bad args");
+    static bool attr_set = false;
+    const int smem = 200 * 1024;
+    if (!attr_set) {
+        UC2_CUDA(cudaFuncSetAttribute(occupy_sms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    occupy_sms_kernel<<<n_ctas, 128, smem, (cudaStream_t)stream>>>(cycles, nullptr);
+    return check_last("occupy_sms_kernel");
+}
+
 extern "C" UC2_API int uc2_gemm_sched_dynamic(int on) {
     const int prev = uc2::gemm_sched_dynamic() ? 1 : 0;
     uc2::g_gemm_dynamic.store(on ? 1 : 0, std::memory_order_relaxed);
