@@ -832,27 +832,32 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                         for (int j = 0; j < 16; j += 4) {
                             const float4 l4 = *reinterpret_cast<const float4*>(lse2 + q_base + c + j);
                             const float4 d4 = *reinterpret_cast<const float4*>(delta + q_base + c + j);
-                            const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq[4] = {d4.x, d4.y, d4.z, d4.w};
-                            float pdv[4], dsv[4];
+                            // two queries per instruction (common.cuh: packed fp32 pairs, same roundings as the scalar
+                            // form): these loops are bound by instruction issue on the scheduler that owns the lane quarter
+                            const f32x2 nlq[2] = {pk2(-l4.x, -l4.y), pk2(-l4.z, -l4.w)};
+                            const f32x2 ndq[2] = {pk2(-d4.x, -d4.y), pk2(-d4.z, -d4.w)};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float pe = fast_ex2(fmaf(__uint_as_float(rs[j + e]), SCALE_LOG2, bias) - lq[e]);
-                                float dp = __uint_as_float(rd[j + e]);
-                                pdv[e] = pe;
+                            for (int e = 0; e < 2; ++e) {
+                                const int je = j + 2 * e;
+                                const f32x2 x = add2(fma2(pk2u(rs[je], rs[je + 1]), splat2(SCALE_LOG2), splat2(bias)), nlq[e]);
+                                float x0, x1;
+                                up2(x, x0, x1);
+                                const f32x2 pe = pk2(fast_ex2(x0), fast_ex2(x1));
+                                f32x2 dp = pk2u(rd[je], rd[je + 1]);
+                                f32x2 pdv = pe;
                                 if (p.drop.thresh) {
-                                    // element (query q_base + c + j + e, key): same stream as the forward
-                                    const float sc = rbase * drop_pow(DROP_CA, j + e) >= t32 ? p.drop.scale : 0.f;   // finite operands only
-                                    pdv[e] = pe * sc;
-                                    dp *= sc;
+                                    // elements (query q_base + c + je (+1), key): same stream as the forward
+                                    const f32x2 sc = pk2(rbase * drop_pow(DROP_CA, je) >= t32 ? p.drop.scale : 0.f,
+                                                         rbase * drop_pow(DROP_CA, je + 1) >= t32 ? p.drop.scale : 0.f);
+                                    pdv = mul2(pe, sc);                                   // finite operands only
+                                    dp = mul2(dp, sc);
                                 }
                                 // dS without the 1/sqrt(64): a power of two commutes with the bf16 rounding, so it is
                                 // applied once per OUTPUT element in the dK / dQ epilogues instead of once per score here
-                                dsv[e] = pe * (dp - dq[e]);
+                                const f32x2 dsv = mul2(pe, add2(dp, ndq[e]));
+                                pd[j / 2 + e] = pack_bf16x2(pdv);
+                                ds[j / 2 + e] = pack_bf16x2(dsv);
                             }
-                            pd[j / 2] = pack_bf16(pdv[0], pdv[1]);
-                            pd[j / 2 + 1] = pack_bf16(pdv[2], pdv[3]);
-                            ds[j / 2] = pack_bf16(dsv[0], dsv[1]);
-                            ds[j / 2 + 1] = pack_bf16(dsv[2], dsv[3]);
                         }
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
