@@ -104,7 +104,7 @@ layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, co
     constexpr int SLOT = XB + HID * 2;                // x row + dy row
     extern __shared__ __align__(128) uint8_t ln_smem[];
     __shared__ float red[3 * HID];
-    __shared__ float2 part_a[LNB_PAIRS][2], part_b[LNB_PAIRS][2];
+    __shared__ float4 part_a[2][LNB_PAIRS][2];      // double buffered by row parity: one barrier per row is enough
     __shared__ __align__(8) unsigned long long bars[LNB_PAIRS * LN_STAGES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = warp >> 1, half = warp & 1;
@@ -138,9 +138,9 @@ layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, co
     float ag[HV], ab[HV], ax[HV];
 #pragma unroll
     for (int i = 0; i < HV; ++i) ag[i] = ab[i] = ax[i] = 0.f;
-    int s = 0;
+    int s = 0, par = 0;
     uint32_t phase = 0;
-    for (long long row = first; row < rows; row += stride) {
+    for (long long row = first; row < rows; row += stride, par ^= 1) {
         ptx::mbar_wait(bar0 + 8 * s, phase);
         float v[HV], d[HV];
         const uint8_t* slot = ln_smem + (pair * LN_STAGES + s) * SLOT;
@@ -155,42 +155,45 @@ layernorm_bwd_kernel(const void* __restrict__ x, const bf16* __restrict__ dy, co
             }
             load4_bf16(reinterpret_cast<const bf16*>(slot + XB) + c, d + 4 * j);
         }
-        // row statistics: sum and sum of squares over this half, combined with the other half's
-        float sx = 0.f, sq = 0.f;
+        // ONE exchange per row: the row statistics (sum x, sum x^2) and both projections of the backward,
+        //   s1 = mean(g dy)   and   s2 = mean(g dy xhat) = rstd (sum(g dy x) - mean sum(g dy)) / H,
+        // are all sums over the raw row, so the pair needs a single reduction and a single barrier per row (the two-phase
+        // form -- statistics, then projections on xhat -- put two dependent shuffle trees and two barriers on every row's
+        // latency chain, and this kernel is latency-bound: profiles/r02b_gelu_gemm_lnbwd_ncu.txt)
+        float sx = 0.f, sq = 0.f, sg = 0.f, sgx = 0.f;
 #pragma unroll
-        for (int i = 0; i < HV; ++i) { sx += v[i]; sq += v[i] * v[i]; }
+        for (int i = 0; i < HV; ++i) {
+            sx += v[i];
+            sq += v[i] * v[i];
+            const float dg = d[i] * g[i];
+            sg += dg;
+            sgx += dg * v[i];
+        }
         sx = warp_sum(sx);
         sq = warp_sum(sq);
-        if (lane == 0) part_a[pair][half] = make_float2(sx, sq);
+        sg = warp_sum(sg);
+        sgx = warp_sum(sgx);
+        if (lane == 0) part_a[par][pair][half] = make_float4(sx, sq, sg, sgx);
         pair_sync(pair);                               // also: both warps hold their copy, the slot can be refilled
         if (loader && row + LN_STAGES * stride < rows) {
             ptx::fence_proxy_async();
             issue(row + LN_STAGES * stride, s);
         }
         if (++s == LN_STAGES) { s = 0; phase ^= 1u; }
-        const float2 pa0 = part_a[pair][0], pa1 = part_a[pair][1];
+        const float4 pa0 = part_a[par][pair][0], pa1 = part_a[par][pair][1];
         const float mean = (pa0.x + pa1.x) * (1.0f / HID);
         const float var = fmaxf((pa0.y + pa1.y) * (1.0f / HID) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
-        float s1 = 0.f, s2 = 0.f;
+        const float sum_g = pa0.z + pa1.z;
+        const float s1 = sum_g * (1.0f / HID);
+        const float s2 = rstd * ((pa0.w + pa1.w) - mean * sum_g) * (1.0f / HID);
 #pragma unroll
         for (int i = 0; i < HV; ++i) {
             v[i] = (v[i] - mean) * rstd;          // xhat
             ag[i] += d[i] * v[i];
             ab[i] += d[i];
-            d[i] *= g[i];
-            s1 += d[i];
-            s2 += d[i] * v[i];
+            d[i] = rstd * (d[i] * g[i] - s1 - v[i] * s2);
         }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane == 0) part_b[pair][half] = make_float2(s1, s2);
-        pair_sync(pair);
-        const float2 pb0 = part_b[pair][0], pb1 = part_b[pair][1];
-        s1 = (pb0.x + pb1.x) * (1.0f / HID);
-        s2 = (pb0.y + pb1.y) * (1.0f / HID);
-#pragma unroll
-        for (int i = 0; i < HV; ++i) d[i] = rstd * (d[i] - s1 - v[i] * s2);
 #pragma unroll
         for (int j = 0; j < 3; ++j) store4_bf16(dx + row * HID + col_h(half, lane, j), d + 4 * j);
         if (dxm) {
