@@ -34,6 +34,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.uc2_version() >= 100
 
 
+def test_runtime_switches_are_host_state():
+    """uc2_gemm_sched_dynamic / uc2_reserve_sms only set host-side state (no device needed) and hand back the previous
+    value; test-support entry points reject bad arguments before touching a device."""
+    lib = ctypes.CDLL(_lib_path())
+    for f in (lib.uc2_gemm_sched_dynamic, lib.uc2_reserve_sms):
+        f.restype, f.argtypes = ctypes.c_int, [ctypes.c_int]
+    prev = lib.uc2_gemm_sched_dynamic(1)
+    assert prev in (0, 1)
+    assert lib.uc2_gemm_sched_dynamic(0) == 1
+    assert lib.uc2_gemm_sched_dynamic(prev) == 0
+    r0 = lib.uc2_reserve_sms(8)
+    assert lib.uc2_reserve_sms(7) == 8          # odd requests are rounded down to CTA pairs
+    assert lib.uc2_reserve_sms(r0) == 6
+    lib.uc2_debug_occupy_sms.restype = ctypes.c_int
+    lib.uc2_debug_occupy_sms.argtypes = [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p]
+    assert lib.uc2_debug_occupy_sms(0, 10, None) < 0
+    assert lib.uc2_debug_occupy_sms(4, -1, None) < 0
+
+
 def test_no_gpu_means_loud_failure():
     """No CPU fallback: a compute entry point on a box without a usable sm_100 device returns an error code,
     and the Python modules raise."""
