@@ -840,3 +840,26 @@ def test_bench_workloads_host_side():
     pb = bench.host_batches("pretrain", seed=3, n=4)
     assert [t for t, _ in pb] == list(bench.TASKS)
     assert all(x["attn_masks"].shape == (4, 160) for _, x in pb)
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the CPU arm: the oracle port of the reference step on the host cores) prints ONE JSON
+    line with the keys the driver reads.  Two layers and one step keep it to well under a minute of host time; the
+    workload shape (64 x (60 + 100), vocabulary 250 002) is the real one."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--layers", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["metric"].startswith("pretrain samples/sec") and d["unit"] == "samples/s"
+    assert d["steps"] == 1 and d["n_gpus"] == 1 and d["value"] > 0
+    assert abs(d["value"] - 64 / (d["ms_per_step"] / 1e3)) <= 1e-6 * d["value"]          # 64 samples per step
+    assert "workload" in d["config"] and d["config"].get("per_gpu_batch") == 64
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
