@@ -17,6 +17,10 @@
 // shared memory, whose bandwidth belongs to the MMAs).  The residual / dGELU operand of a tile is requested
 // BEFORE the accumulator is complete, so those loads fly while the MMAs of the tile still run, and the
 // epilogue of tile i hides under the MMAs of tile i+1 (two accumulator buffers).
+//
+// Tile order: fixed round-robin over the persistent workers, or (uc2_gemm_sched_dynamic, on under data parallelism)
+// drawn from a per-launch device counter and handed to the roles through a shared-memory ring -- see SCHED_R.
+// The GELU / GELU' epilogues evaluate two columns per instruction on packed fp32 pairs (common.cuh: gelu_erf2).
 #include <mutex>
 
 #include "common.cuh"
