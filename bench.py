@@ -390,7 +390,7 @@ def run_retrieval(args, rank, world, steps=None, warmup=None):
             "config": {"workload": f"COCO-scale text-to-image retrieval scoring: one step = 1 caption (tl ~ U{CAP_RANGE}, mean "
                                    f"{tl_mean:.1f}) x {N_IMAGES} images (10-100 regions, sorted, chunks of {INF_MB}) per GPU; "
                                    "caption rows sharded over ranks (itm.py:492-538)",
-                       "model": "uc2-base 12L/768H vocab 250002 random init", "per_gpu_pairs_per_step": N_IMAGES,
+                       "encoder": "uc2-base 12L/768H, vocabulary 250002, random init", "per_gpu_pairs_per_step": N_IMAGES,
                        "l2": "2.3 GB of fp32 region features streamed per step, far above the 126 MB L2",
                        "timing": "faster of two regions of `steps` steps (host-driven: ~1 150 launches per step)"},
             "e2e": {"value": N_IMAGES * world / (ms_e2e / 1e3), "unit": "pair-scores/s", "ms_per_step": ms_e2e,
@@ -597,7 +597,7 @@ def run_training(args, workload, rank, world, steps, warmup, with_cpu, with_stor
     line = {"metric": W["metric"], "unit": "samples/s", "value": per_gpu * world / (ms_step / 1e3), "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": W["name"], "model": "uc2-base 12L/768H vocab 250002 random init",
+            "config": {"workload": W["name"], "encoder": "uc2-base 12L/768H, vocabulary 250002, random init",
                        "per_gpu_batch": per_gpu, "seq_len": S, "dropout": args.dropout, "weight_decay": WEIGHT_DECAY,
                        "gradient_accumulation_steps": 1,
                        "optimizer": "AdamW, eager" if args.eager_adamw else
@@ -634,7 +634,7 @@ def reference_line(args):
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": "COCO-scale text-to-image retrieval scoring (itm.py:492-538): (caption, image) "
-                                       "pairs, tl 19, 10-100 regions", "model": "uc2-base 12L/768H vocab 250002 random init"},
+                                       "pairs, tl 19, 10-100 regions", "encoder": "uc2-base 12L/768H, vocabulary 250002, random init"},
                 "cpu_baseline": {"value": val, "unit": "pair-scores/s", "cores": os.cpu_count(), "kind": "port",
                                  "sample": f"{n} (caption, image) pairs per step (oracle port, fp32, all host threads)"},
                 "e2e": {"value": val, "unit": "pair-scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -643,7 +643,7 @@ def reference_line(args):
     return {"metric": W["metric"], "unit": "samples/s", "impl": "reference", "value": val, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": W["name"], "model": "uc2-base 12L/768H vocab 250002 random init",
+            "config": {"workload": W["name"], "encoder": "uc2-base 12L/768H, vocabulary 250002, random init",
                        "per_gpu_batch": n, "seq_len": W["S"], "dropout": args.dropout, "weight_decay": WEIGHT_DECAY,
                        "gradient_accumulation_steps": 1,
                        "l2": "working set (1.1 GB fp32 params + >5 GB activations per step) far exceeds the 126 MB L2"},
